@@ -1,0 +1,914 @@
+/*
+ * volprim_oracle.c -- CPU restatement of the reference's per-ray volumetric-primitive
+ * integration loop (volprim_rf / volprim_tomography).
+ *
+ * THIS FILE IS TEST INFRASTRUCTURE.  It is the parity checker for the CUDA path and the
+ * CPU baseline of bench.py; nothing in the product package (volprim_balance_b200/) may
+ * import, link or call it.
+ *
+ * PARITY PINNING.  The reference ships no tests and no golden vectors, and its third-party
+ * halves (Mitsuba 3 `ellipsoids_release` branch, Dr.Jit) are not in /root/reference and
+ * cannot be installed here.  What pins this file:
+ *   - tests/golden/kernels_*.npz, sample_*.npz: outputs of the reference's OWN Python source
+ *     (volprim/integrators/common.py, volprim_rf.py, volprim_tomography.py) executed in the
+ *     authoring container over a torch-backed stand-in for the drjit/mitsuba API
+ *     (tests/golden/make_golden.py).  That pins every formula that lives in /root/reference:
+ *     kernel eval / density integrals / ray-ellipsoid quadratic / the two sample() loops and
+ *     their PRB adjoints (gradients obtained by torch autograd through the reference code).
+ *   - The third-party pieces (closest-hit query semantics, dr.sh_eval, dr.quat_to_matrix,
+ *     mi.math.srgb_to_linear, improved_solve_quadratic) are restated from their published
+ *     definitions; for those, PARITY IS UNPINNED ("Decisions").
+ *
+ * Each function cites the reference file:line it follows (paths relative to /root/reference).
+ *
+ * The file is compiled twice (oracle/Makefile): REAL=float -> liboracle_f32.so (the parity
+ * oracle proper: same precision as the reference's Float), REAL=double -> liboracle_f64.so
+ * (finite-difference gradients, tolerance studies).  Compile with -ffp-contract=off so that
+ * the evaluation order written here is the evaluation order executed.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef REAL
+#define REAL float
+#endif
+
+#define CAT_(a, b) a##b
+#define CAT(a, b) CAT_(a, b)
+
+#ifdef ORACLE_F64
+#define EXP(x) exp(x)
+#define SQRT(x) sqrt(x)
+#define POW(x, y) pow(x, y)
+#define FMA(a, b, c) fma(a, b, c)
+#define FABS(x) fabs(x)
+#define COPYSIGN(a, b) copysign(a, b)
+#define REAL_MAX DBL_MAX
+#else
+#define EXP(x) expf(x)
+#define SQRT(x) sqrtf(x)
+#define POW(x, y) powf(x, y)
+#define FMA(a, b, c) fmaf(a, b, c)
+#define FABS(x) fabsf(x)
+#define COPYSIGN(a, b) copysignf(a, b)
+#define REAL_MAX FLT_MAX
+#endif
+
+#define R_(x) ((REAL)(x))
+#define PI_D 3.14159265358979323846
+
+enum { ORC_RF = 0, ORC_TOMO = 1 };
+enum { ORC_GAUSS = 0, ORC_EPAN = 1 };
+
+typedef struct {
+    int32_t integrator;      /* ORC_RF | ORC_TOMO */
+    int32_t kernel;          /* ORC_GAUSS | ORC_EPAN          common.py:96-105 */
+    uint32_t max_depth;      /* 0xFFFFFFFF == unlimited        volprim_rf.py:26-29 */
+    int32_t srgb_primitives; /*                                volprim_rf.py:41 */
+    int32_t hide_emitters;   /*                                volprim_tomography.py:106 */
+    int32_t brute_force;     /* 1: O(N) closest-hit search instead of the CPU BVH */
+    int32_t diagnostics;     /* 1: keep searching to the second-closest entry (fragility report) */
+    int32_t pad_;
+    double t_cutoff;         /* 0.01                           volprim_rf.py:173-174 */
+    double eps_advance;      /* 1e-4                           volprim_rf.py:149 */
+    double env[3];           /* constant environment radiance  volprim_tomography.py:107 */
+} orc_params;
+
+typedef struct {
+    float lo[3], hi[3];
+    int32_t left, right; /* internal: child node indices; leaf: left = first, right = -count */
+} orc_node;
+
+typedef struct {
+    int64_t n;
+    int32_t sh_floats; /* C = 3 (D+1)^2, 0 if none */
+    int32_t sh_degree;
+    REAL extent;
+    REAL *data; /* [n*10] center3, scale3, quat(i,j,k,r)   common.py:47-74 */
+    REAL *attr; /* [n]    opacities (rf) or sigma_t (tomo) */
+    REAL *sh;   /* [n*C]  coefficient-major, channel-minor   volprim_rf.py:91-95 */
+    /* CPU BVH (oracle-internal accelerator; results must equal brute force) */
+    orc_node *nodes;
+    int32_t *order;
+    int64_t n_nodes;
+    float *blo, *bhi; /* per-primitive padded AABBs */
+} orc_scene;
+
+/* ------------------------------------------------------------------------------------------
+ * Third-party restatements (PARITY UNPINNED -- definitions from the published libraries)
+ * ---------------------------------------------------------------------------------------- */
+
+/* dr.quat_to_matrix(q, size=3) with q = (x, y, z, w), NOT normalised (common.py:73,86). */
+static void quat_to_matrix(const REAL q[4], REAL R[3][3])
+{
+    REAL x = q[0], y = q[1], z = q[2], w = q[3];
+    REAL xx = x * x, yy = y * y, zz = z * z;
+    REAL xy = x * y, xz = x * z, yz = y * z;
+    REAL xw = x * w, yw = y * w, zw = z * w;
+    R[0][0] = R_(1) - R_(2) * (yy + zz);
+    R[0][1] = R_(2) * (xy - zw);
+    R[0][2] = R_(2) * (xz + yw);
+    R[1][0] = R_(2) * (xy + zw);
+    R[1][1] = R_(1) - R_(2) * (xx + zz);
+    R[1][2] = R_(2) * (yz - xw);
+    R[2][0] = R_(2) * (xz - yw);
+    R[2][1] = R_(2) * (yz + xw);
+    R[2][2] = R_(1) - R_(2) * (xx + yy);
+}
+
+/* rot.T * v */
+static void rot_t_mul(const REAL R[3][3], const REAL v[3], REAL out[3])
+{
+    for (int i = 0; i < 3; ++i)
+        out[i] = (R[0][i] * v[0] + R[1][i] * v[1]) + R[2][i] * v[2];
+}
+
+/* mi.math.srgb_to_linear (volprim_rf.py:190) */
+static REAL srgb_to_linear(REAL x)
+{
+    if (x <= R_(0.04045)) return x / R_(12.92);
+    return POW((x + R_(0.055)) / R_(1.055), R_(2.4));
+}
+static REAL srgb_to_linear_deriv(REAL x)
+{
+    if (x <= R_(0.04045)) return R_(1) / R_(12.92);
+    return R_(2.4) / R_(1.055) * POW((x + R_(0.055)) / R_(1.055), R_(1.4));
+}
+
+/* dr.sh_eval(d, degree): real SH, Sloan "Efficient Spherical Harmonic Evaluation" recurrences
+ * with the Condon-Shortley sign Dr.Jit applies (identical to the 3DGS constants for unit d);
+ * index = l(l+1)+m (scripts/radiosity/sh_utils.py:5-30).  volprim_rf.py:90 */
+static void sh_eval(const REAL d[3], int degree, REAL *Y)
+{
+    REAL x = d[0], y = d[1], z = d[2];
+    Y[0] = R_(0.28209479177387814);
+    if (degree < 1) return;
+    Y[2] = R_(0.48860251190291992) * z;
+    Y[3] = R_(-0.48860251190291992) * x;
+    Y[1] = R_(-0.48860251190291992) * y;
+    if (degree < 2) return;
+    REAL z2 = z * z;
+    Y[6] = R_(0.94617469575756008) * z2 + R_(-0.31539156525251999);
+    REAL tb = R_(-1.0925484305920792) * z;
+    Y[7] = tb * x;
+    Y[5] = tb * y;
+    REAL c1 = x * x - y * y, s1 = x * y + y * x;
+    Y[8] = R_(0.54627421529603959) * c1;
+    Y[4] = R_(0.54627421529603959) * s1;
+    if (degree < 3) return;
+    Y[12] = z * (R_(1.8658816629505769) * z2 + R_(-1.1195289977703462));
+    REAL tc = R_(-2.2852289973223288) * z2 + R_(0.45704579946446572);
+    Y[13] = tc * x;
+    Y[11] = tc * y;
+    REAL td = R_(1.4453057213202769) * z;
+    Y[14] = td * c1;
+    Y[10] = td * s1;
+    REAL c2 = x * c1 - y * s1, s2 = x * s1 + y * c1;
+    Y[15] = R_(-0.59004358992664352) * c2;
+    Y[9] = R_(-0.59004358992664352) * s2;
+}
+
+/* mi.math.improved_solve_quadratic(a, b, c, discr) as used at common.py:365:
+ * b is the NEGATED half linear coefficient, discr the RT-Gems-2 discriminant. */
+static int improved_solve_quadratic(REAL a, REAL b, REAL c, REAL discr, REAL *t0, REAL *t1)
+{
+    if (!(discr >= R_(0)) || a == R_(0)) return 0;
+    REAL sq = SQRT(a * discr);
+    REAL q = b + COPYSIGN(sq, b);
+    REAL x0 = c / q;
+    REAL x1 = q / a;
+    if (x0 <= x1) { *t0 = x0; *t1 = x1; } else { *t0 = x1; *t1 = x0; }
+    return isfinite((double)*t0) && isfinite((double)*t1);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Reference-owned formulas
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct {
+    REAL c[3], s[3], q[4], R[3][3], extent;
+} ellipsoid;
+
+/* Ellipsoid.gather (common.py:76-91): 10-float record + rot = quat_to_matrix(quat) */
+static void gather(const orc_scene *sc, int64_t j, ellipsoid *e)
+{
+    const REAL *p = sc->data + j * 10;
+    for (int i = 0; i < 3; ++i) { e->c[i] = p[i]; e->s[i] = p[3 + i]; }
+    for (int i = 0; i < 4; ++i) e->q[i] = p[6 + i];
+    quat_to_matrix(e->q, e->R);
+    e->extent = sc->extent;
+}
+
+/* ray_ellipsoid_intersection (common.py:346-367), the `else` (RT Gems 2) branch. */
+static int ray_ellipsoid(const REAL o[3], const REAL d[3], const ellipsoid *e, REAL *tn, REAL *tf,
+                         REAL *discr_out)
+{
+    REAL sc[3], v[3], rd[3], ro[3], dd[3], oo[3];
+    for (int i = 0; i < 3; ++i) { sc[i] = e->s[i] * e->extent; v[i] = o[i] - e->c[i]; }
+    rot_t_mul(e->R, d, rd);
+    rot_t_mul(e->R, v, ro);
+    for (int i = 0; i < 3; ++i) { dd[i] = rd[i] / sc[i]; oo[i] = ro[i] / sc[i]; }
+    REAL a = (dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2];
+    REAL b = -((oo[0] * dd[0] + oo[1] * dd[1]) + oo[2] * dd[2]);
+    REAL c = ((oo[0] * oo[0] + oo[1] * oo[1]) + oo[2] * oo[2]) - R_(1);
+    REAL ba = b / a;
+    REAL l0 = oo[0] + ba * dd[0], l1 = oo[1] + ba * dd[1], l2 = oo[2] + ba * dd[2];
+    REAL discr = R_(1) - ((l0 * l0 + l1 * l1) + l2 * l2);
+    if (discr_out) *discr_out = discr;
+    return improved_solve_quadratic(a, b, c, discr, tn, tf);
+}
+
+/* GaussianKernel.eval (common.py:153-159) */
+static REAL gaussian_eval(const REAL p[3], const ellipsoid *e)
+{
+    REAL v[3] = { p[0] - e->c[0], p[1] - e->c[1], p[2] - e->c[2] }, r[3];
+    rot_t_mul(e->R, v, r);
+    const REAL *s = e->s;
+    REAL qq = ((r[0] * r[0]) / (s[0] * s[0]) + (r[1] * r[1]) / (s[1] * s[1])) + (r[2] * r[2]) / (s[2] * s[2]);
+    return EXP(R_(-0.5) * qq);
+}
+
+/* EpanechnikovKernel.eval (common.py:251-259): support 3*scale, peak 0.75 */
+static REAL epanechnikov_eval(const REAL p[3], const ellipsoid *e)
+{
+    REAL v[3] = { p[0] - e->c[0], p[1] - e->c[1], p[2] - e->c[2] }, r[3];
+    rot_t_mul(e->R, v, r);
+    for (int i = 0; i < 3; ++i) r[i] = r[i] / (e->s[i] * R_(3));
+    REAL dist = SQRT((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]);
+    REAL value = R_(0.75) * (R_(1) - dist * dist);
+    return value > R_(0) ? value : R_(0);
+}
+
+/* GaussianKernel.density_integral, full-range branch, normalized=False
+ * (common.py:199-206, 238-243).  Returns the clamped value; *raw gets the unclamped one. */
+static REAL gaussian_density_integral(const REAL o[3], const REAL d[3], const ellipsoid *e, REAL *raw)
+{
+    REAL v[3] = { o[0] - e->c[0], o[1] - e->c[1], o[2] - e->c[2] }, w[3], p[3];
+    rot_t_mul(e->R, d, w);
+    rot_t_mul(e->R, v, p);
+    REAL sx2 = e->s[0] * e->s[0], sy2 = e->s[1] * e->s[1], sz2 = e->s[2] * e->s[2];
+    REAL wx2 = w[0] * w[0], wy2 = w[1] * w[1], wz2 = w[2] * w[2];
+    REAL px2 = p[0] * p[0], py2 = p[1] * p[1], pz2 = p[2] * p[2];
+    REAL C1 = (sx2 * sy2 * wz2 + sx2 * sz2 * wy2) + sy2 * sz2 * wx2;
+    REAL num = ((((px2 * sy2 + py2 * sx2) * wz2
+                  - R_(2) * p[2] * w[2] * (p[1] * sx2 * w[1] + p[0] * sy2 * w[0]))
+                 + wy2 * (px2 * sz2 + pz2 * sx2))
+                - R_(2) * p[0] * p[1] * sz2 * w[0] * w[1])
+               + wx2 * (py2 * sz2 + pz2 * sy2);
+    REAL exponent = num / (R_(2) * C1);
+    REAL denom = R_(2) * R_(PI_D) * SQRT(C1);
+    REAL density = EXP(-exponent) / denom;
+    if (raw) *raw = density;
+    if (!(density > R_(0))) density = R_(0);       /* dr.maximum(density, 0); NaN -> 0 below */
+    if (!isfinite((double)density)) density = R_(0);
+    return density;
+}
+
+/* EpanechnikovKernel.density_integral, full-range branch, normalized=False
+ * (common.py:287-324).  Bandwidth s over the extent*s chord, kernel not clamped (quirk Q4). */
+static REAL epanechnikov_density_integral(const REAL o[3], const REAL d[3], const ellipsoid *e, REAL *raw)
+{
+    REAL tmin, tmax;
+    if (raw) *raw = R_(0);
+    int valid = ray_ellipsoid(o, d, e, &tmin, &tmax, NULL);
+    if (!valid || !(tmin < tmax) || !(tmax > R_(0))) return R_(0);
+    REAL a0[3], a1[3], p[3], p1[3], w[3];
+    for (int i = 0; i < 3; ++i) {
+        a0[i] = FMA(d[i], tmin, o[i]) - e->c[i];
+        a1[i] = FMA(d[i], tmax, o[i]) - e->c[i];
+    }
+    rot_t_mul(e->R, a0, p);
+    rot_t_mul(e->R, a1, p1);
+    for (int i = 0; i < 3; ++i) w[i] = p1[i] - p[i];
+    REAL t = SQRT((w[0] * w[0] + w[1] * w[1]) + w[2] * w[2]);
+    for (int i = 0; i < 3; ++i) w[i] = w[i] / t;
+    REAL sx2 = e->s[0] * e->s[0], sy2 = e->s[1] * e->s[1], sz2 = e->s[2] * e->s[2];
+    REAL t2 = t * t, t3 = t2 * t;
+    REAL poly = sx2 * sy2 * t3 * (w[2] * w[2])
+              + R_(3) * p[2] * sx2 * sy2 * t2 * w[2]
+              + sx2 * sz2 * t3 * (w[1] * w[1])
+              + R_(3) * p[1] * sx2 * sz2 * t2 * w[1]
+              + sy2 * sz2 * t3 * (w[0] * w[0])
+              + R_(3) * p[0] * sy2 * sz2 * t2 * w[0]
+              + (((R_(3) * (p[0] * p[0]) - R_(3) * sx2) * sy2 + R_(3) * (p[1] * p[1]) * sx2) * sz2
+                 + R_(3) * (p[2] * p[2]) * sx2 * sy2) * t;
+    REAL s3 = (e->s[0] * e->s[0] * e->s[0]) * (e->s[1] * e->s[1] * e->s[1]) * (e->s[2] * e->s[2] * e->s[2]);
+    REAL density = -poly * R_(5) / (R_(8) * R_(PI_D) * s3);
+    if (raw) *raw = density;
+    if (!(density > R_(0))) density = R_(0);
+    if (!isfinite((double)density)) density = R_(0);
+    return density;
+}
+
+/* volprim_rf.eval_transmission (volprim_rf.py:63-80): returns T, also alpha_raw=opacity*density and G */
+static REAL rf_transmission(const REAL o[3], const REAL d[3], const ellipsoid *e, REAL opacity, int kernel,
+                            REAL *G_out, REAL *ppeak_out)
+{
+    REAL v[3] = { o[0] - e->c[0], o[1] - e->c[1], o[2] - e->c[2] }, ro[3], rd[3], oo[3], dd[3];
+    rot_t_mul(e->R, v, ro);
+    rot_t_mul(e->R, d, rd);
+    for (int i = 0; i < 3; ++i) { oo[i] = ro[i] / e->s[i]; dd[i] = rd[i] / e->s[i]; }
+    REAL od = (oo[0] * dd[0] + oo[1] * dd[1]) + oo[2] * dd[2];
+    REAL dd2 = (dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2];
+    REAL t_peak = -od / dd2;
+    REAL pp[3];
+    for (int i = 0; i < 3; ++i) pp[i] = FMA(d[i], t_peak, o[i]);
+    REAL G = (kernel == ORC_GAUSS) ? gaussian_eval(pp, e) : epanechnikov_eval(pp, e);
+    if (G_out) *G_out = G;
+    if (ppeak_out) { ppeak_out[0] = pp[0]; ppeak_out[1] = pp[1]; ppeak_out[2] = pp[2]; }
+    REAL a = opacity * G;
+    if (!(a < R_(0.9999))) a = R_(0.9999); /* dr.minimum; NaN propagates in Dr.Jit as min(NaN,c)=c */
+    return R_(1) - a;
+}
+
+/* volprim_rf.eval_sh_emission (volprim_rf.py:82-100): max(sum_i Y_i f_i + 0.5, 0) */
+static void rf_emission(const orc_scene *sc, int64_t j, const REAL *Y, REAL col[3], REAL raw[3])
+{
+    int nb = sc->sh_floats / 3;
+    const REAL *f = sc->sh + j * sc->sh_floats;
+    REAL e[3] = { R_(0), R_(0), R_(0) };
+    for (int i = 0; i < nb; ++i)
+        for (int ch = 0; ch < 3; ++ch) e[ch] += Y[i] * f[3 * i + ch];
+    for (int ch = 0; ch < 3; ++ch) {
+        raw[ch] = e[ch] + R_(0.5);
+        col[ch] = raw[ch] > R_(0) ? raw[ch] : R_(0);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Closest front-face hit query  (third-party scene.ray_intersect; semantics = DESIGN decision 1:
+ * analytic ellipsoid at extent*scale, back faces culled, 0 < t <= maxt, ties -> lowest index)
+ * volprim_rf.py:124-129, volprim_tomography.py:71-76
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct {
+    int64_t id;
+    REAL t;
+    /* diagnostics for the parity tests: how fragile was this decision under fp32 rounding? */
+    REAL second_t;   /* next-closest valid entry (REAL_MAX if none) */
+    REAL min_abs_t;  /* smallest |t_near| over primitives straddling the origin cull */
+    REAL min_abs_discr; /* smallest |discr| over primitives tested whose box was entered */
+} hit_rec;
+
+static inline void consider(const orc_scene *sc, int64_t j, const REAL o[3], const REAL d[3], REAL maxt,
+                            hit_rec *h)
+{
+    ellipsoid e;
+    gather(sc, j, &e);
+    REAL tn, tf, discr;
+    int valid = ray_ellipsoid(o, d, &e, &tn, &tf, &discr);
+    if (FABS(discr) < h->min_abs_discr) h->min_abs_discr = FABS(discr);
+    if (!valid) return;
+    if (FABS(tn) < h->min_abs_t) h->min_abs_t = FABS(tn);
+    if (!(tn > R_(0)) || !(tn <= maxt)) return; /* front face behind origin => culled */
+    if (tn < h->t || (tn == h->t && j < h->id)) {
+        if (h->id >= 0 && h->t < h->second_t) h->second_t = h->t;
+        h->t = tn;
+        h->id = j;
+    } else if (tn < h->second_t) {
+        h->second_t = tn;
+    }
+}
+
+static void prim_aabb(const orc_scene *sc, int64_t j, float lo[3], float hi[3])
+{
+    /* bounds of { x : |diag(1/(extent s)) R^T (x - c)| = 1 } = c + R^{-T} diag(extent s) u, |u| = 1,
+     * evaluated in double and padded; valid for non-orthonormal R (un-normalised quaternions, Q6). */
+    const REAL *p = sc->data + j * 10;
+    double x = p[6], y = p[7], z = p[8], w = p[9];
+    double R[3][3] = {
+        { 1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w) },
+        { 2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w) },
+        { 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y) } };
+    /* B = R^{-T}: cofactor inverse of R^T */
+    double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1])
+               - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0])
+               + R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+    double inv[3][3]; /* inverse of R */
+    inv[0][0] = (R[1][1] * R[2][2] - R[1][2] * R[2][1]) / det;
+    inv[0][1] = (R[0][2] * R[2][1] - R[0][1] * R[2][2]) / det;
+    inv[0][2] = (R[0][1] * R[1][2] - R[0][2] * R[1][1]) / det;
+    inv[1][0] = (R[1][2] * R[2][0] - R[1][0] * R[2][2]) / det;
+    inv[1][1] = (R[0][0] * R[2][2] - R[0][2] * R[2][0]) / det;
+    inv[1][2] = (R[0][2] * R[1][0] - R[0][0] * R[1][2]) / det;
+    inv[2][0] = (R[1][0] * R[2][1] - R[1][1] * R[2][0]) / det;
+    inv[2][1] = (R[0][1] * R[2][0] - R[0][0] * R[2][1]) / det;
+    inv[2][2] = (R[0][0] * R[1][1] - R[0][1] * R[1][0]) / det;
+    for (int i = 0; i < 3; ++i) {
+        /* (R^{-T})_{ik} = inv[k][i] */
+        double h2 = 0;
+        for (int k = 0; k < 3; ++k) {
+            double b = inv[k][i] * (double)p[3 + k] * (double)sc->extent;
+            h2 += b * b;
+        }
+        double h = sqrt(h2);
+        if (!isfinite(h)) h = 1e30;
+        double pad = 1e-4 * h + 1e-6 * (fabs((double)p[i]) + 1.0);
+        lo[i] = (float)((double)p[i] - h - pad);
+        hi[i] = (float)((double)p[i] + h + pad);
+    }
+}
+
+/* ---- oracle-internal CPU BVH: top-down median split on centroids, leaves of <= 4 ---- */
+typedef struct { orc_scene *sc; float *cent; } build_ctx;
+
+static int64_t build_rec(build_ctx *bc, int64_t first, int64_t count)
+{
+    orc_scene *sc = bc->sc;
+    int64_t me = sc->n_nodes++;
+    orc_node *nd = &sc->nodes[me];
+    float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    float clo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, chi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (int64_t k = first; k < first + count; ++k) {
+        int64_t j = sc->order[k];
+        for (int a = 0; a < 3; ++a) {
+            if (sc->blo[3 * j + a] < lo[a]) lo[a] = sc->blo[3 * j + a];
+            if (sc->bhi[3 * j + a] > hi[a]) hi[a] = sc->bhi[3 * j + a];
+            float c = bc->cent[3 * j + a];
+            if (c < clo[a]) clo[a] = c;
+            if (c > chi[a]) chi[a] = c;
+        }
+    }
+    memcpy(nd->lo, lo, sizeof lo);
+    memcpy(nd->hi, hi, sizeof hi);
+    if (count <= 4) { nd->left = (int32_t)first; nd->right = -(int32_t)count; return me; }
+    int ax = 0;
+    if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+    if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+    float mid = 0.5f * (clo[ax] + chi[ax]);
+    int64_t i = first, k = first + count - 1;
+    while (i <= k) {
+        if (bc->cent[3 * sc->order[i] + ax] < mid) ++i;
+        else { int32_t tmp = sc->order[i]; sc->order[i] = sc->order[k]; sc->order[k] = tmp; --k; }
+    }
+    int64_t nl = i - first;
+    if (nl == 0 || nl == count) nl = count / 2;
+    int64_t l = build_rec(bc, first, nl);
+    int64_t r = build_rec(bc, first + nl, count - nl);
+    nd = &sc->nodes[me];
+    nd->left = (int32_t)l;
+    nd->right = (int32_t)r;
+    return me;
+}
+
+static int box_hit(const orc_node *nd, const double o[3], const double inv[3], double tmin, double tmax,
+                   double *tenter)
+{
+    double t0 = tmin, t1 = tmax;
+    for (int a = 0; a < 3; ++a) {
+        double ta = ((double)nd->lo[a] - o[a]) * inv[a];
+        double tb = ((double)nd->hi[a] - o[a]) * inv[a];
+        if (ta > tb) { double tt = ta; ta = tb; tb = tt; }
+        if (ta > t0) t0 = ta;
+        if (tb < t1) t1 = tb;
+    }
+    *tenter = t0;
+    return t0 <= t1;
+}
+
+static void closest_hit(const orc_scene *sc, const orc_params *pr, const REAL o[3], const REAL d[3], REAL maxt,
+                        hit_rec *h)
+{
+    h->id = -1;
+    h->t = REAL_MAX;
+    h->second_t = REAL_MAX;
+    h->min_abs_t = REAL_MAX;
+    h->min_abs_discr = REAL_MAX;
+    if (pr->brute_force || sc->nodes == NULL) {
+        for (int64_t j = 0; j < sc->n; ++j) consider(sc, j, o, d, maxt, h);
+        return;
+    }
+    double od[3] = { o[0], o[1], o[2] }, inv[3];
+    double dn = sqrt((double)d[0] * d[0] + (double)d[1] * d[1] + (double)d[2] * d[2]);
+    for (int a = 0; a < 3; ++a) {
+        double da = d[a];
+        if (fabs(da) < 1e-30) da = da < 0 ? -1e-30 : 1e-30;
+        inv[a] = 1.0 / da;
+    }
+    /* the box interval reaches slightly behind the origin so that the fragility diagnostics see the
+     * primitives that straddle the back-face cull; the hit itself is decided in consider(). */
+    double back = pr->diagnostics ? -1e-3 / (dn > 0 ? dn : 1.0) : 0.0;
+    int32_t stack[128];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp) {
+        const orc_node *nd = &sc->nodes[stack[--sp]];
+        double te;
+        REAL cut = pr->diagnostics ? h->second_t : h->t;
+        double lim = (cut < REAL_MAX) ? (double)cut * (1 + 1e-5) + 1e-6
+                                              : (maxt < REAL_MAX ? (double)maxt * (1 + 1e-5) + 1e-6 : 1e300);
+        if (!box_hit(nd, od, inv, back, lim, &te)) continue;
+        if (nd->right < 0) {
+            for (int32_t k = 0; k < -nd->right; ++k) consider(sc, sc->order[nd->left + k], o, d, maxt, h);
+        } else {
+            double tl, tr;
+            int hl = box_hit(&sc->nodes[nd->left], od, inv, back, lim, &tl);
+            int hr = box_hit(&sc->nodes[nd->right], od, inv, back, lim, &tr);
+            if (hl && hr) {
+                if (tl <= tr) { stack[sp++] = nd->right; stack[sp++] = nd->left; }
+                else { stack[sp++] = nd->left; stack[sp++] = nd->right; }
+            } else if (hl) stack[sp++] = nd->left;
+            else if (hr) stack[sp++] = nd->right;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Exported API
+ * ---------------------------------------------------------------------------------------- */
+#define EXPORT __attribute__((visibility("default")))
+
+EXPORT int orc_real_size(void) { return (int)sizeof(REAL); }
+
+EXPORT void orc_scene_free(orc_scene *sc)
+{
+    if (!sc) return;
+    free(sc->data); free(sc->attr); free(sc->sh); free(sc->nodes); free(sc->order); free(sc->blo); free(sc->bhi);
+    free(sc);
+}
+
+EXPORT orc_scene *orc_scene_create(int64_t n, const REAL *data10, const REAL *attr, const REAL *sh, int32_t sh_floats,
+                                   double extent, int32_t build_bvh)
+{
+    orc_scene *sc = (orc_scene *)calloc(1, sizeof *sc);
+    sc->n = n;
+    sc->sh_floats = sh ? sh_floats : 0;
+    sc->sh_degree = -1;
+    if (sc->sh_floats) {
+        /* sh_degree = int(sqrt(C // 3 - 1))  -- volprim_rf.py:89, reproduced literally */
+        sc->sh_degree = (int)sqrt((double)(sc->sh_floats / 3 - 1));
+    }
+    sc->extent = (REAL)extent;
+    sc->data = (REAL *)malloc(sizeof(REAL) * (size_t)(n > 0 ? n : 1) * 10);
+    memcpy(sc->data, data10, sizeof(REAL) * (size_t)n * 10);
+    sc->attr = (REAL *)malloc(sizeof(REAL) * (size_t)(n > 0 ? n : 1));
+    if (attr) memcpy(sc->attr, attr, sizeof(REAL) * (size_t)n);
+    else for (int64_t i = 0; i < n; ++i) sc->attr[i] = R_(1);
+    if (sc->sh_floats) {
+        sc->sh = (REAL *)malloc(sizeof(REAL) * (size_t)n * sc->sh_floats);
+        memcpy(sc->sh, sh, sizeof(REAL) * (size_t)n * sc->sh_floats);
+    }
+    if (build_bvh && n > 0) {
+        sc->blo = (float *)malloc(sizeof(float) * 3 * (size_t)n);
+        sc->bhi = (float *)malloc(sizeof(float) * 3 * (size_t)n);
+        float *cent = (float *)malloc(sizeof(float) * 3 * (size_t)n);
+        sc->order = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+        for (int64_t j = 0; j < n; ++j) {
+            prim_aabb(sc, j, sc->blo + 3 * j, sc->bhi + 3 * j);
+            for (int a = 0; a < 3; ++a) cent[3 * j + a] = (float)sc->data[j * 10 + a];
+            sc->order[j] = (int32_t)j;
+        }
+        sc->nodes = (orc_node *)malloc(sizeof(orc_node) * (size_t)(2 * n + 1));
+        sc->n_nodes = 0;
+        build_ctx bc = { sc, cent };
+        build_rec(&bc, 0, n);
+        free(cent);
+    }
+    return sc;
+}
+
+/* one primitive interaction of the rf loop; returns T. */
+typedef struct {
+    REAL T, G, one_minus_T, col[3], colraw[3], Le[3], ppeak[3];
+    int le_finite[3];
+} rf_hit;
+
+static void rf_interact(const orc_scene *sc, const orc_params *pr, int64_t j, const REAL o[3], const REAL d[3],
+                        const REAL *Y, REAL beta, rf_hit *r)
+{
+    ellipsoid e;
+    gather(sc, j, &e);
+    r->T = rf_transmission(o, d, &e, sc->attr[j], pr->kernel, &r->G, r->ppeak);
+    if (sc->sh_floats) rf_emission(sc, j, Y, r->col, r->colraw);
+    else for (int ch = 0; ch < 3; ++ch) { r->col[ch] = R_(0); r->colraw[ch] = R_(0); } /* volprim_rf.py:98-99 */
+    r->one_minus_T = R_(1) - r->T;
+    for (int ch = 0; ch < 3; ++ch) {
+        REAL le = beta * r->one_minus_T * r->col[ch]; /* volprim_rf.py:140 */
+        r->le_finite[ch] = isfinite((double)le);
+        r->Le[ch] = r->le_finite[ch] ? le : R_(0);    /* volprim_rf.py:141 */
+    }
+}
+
+static REAL tomo_interact(const orc_scene *sc, const orc_params *pr, int64_t j, const REAL o[3], const REAL d[3],
+                          REAL *rho_out, REAL *raw_out)
+{
+    ellipsoid e;
+    gather(sc, j, &e);
+    REAL raw;
+    REAL rho = (pr->kernel == ORC_GAUSS) ? gaussian_density_integral(o, d, &e, &raw)
+                                         : epanechnikov_density_integral(o, d, &e, &raw);
+    if (rho_out) *rho_out = rho;
+    if (raw_out) *raw_out = raw;
+    return EXP(-rho * sc->attr[j]); /* volprim_tomography.py:44 */
+}
+
+/*
+ * Forward loop.  volprim_rf.py:103-192, volprim_tomography.py:47-127.
+ * Outputs (any may be NULL): rgb [R*3]; beta [R]; nhits [R]; hit_ids [R*cap] (-1 padded);
+ * hit_t [R*cap] distance of each accepted entry from the ORIGINAL origin (double, diagnostics);
+ * fragility [R*3]: per ray min(second_t - t), min |t_near| at the cull, min |discr|.
+ */
+EXPORT void orc_trace_forward(const orc_scene *sc, const orc_params *pr, int64_t R, const REAL *ray_o,
+                              const REAL *ray_d, const REAL *ray_maxt, REAL *rgb, REAL *beta_out, uint32_t *nhits,
+                              int32_t *hit_ids, double *hit_t, int32_t cap, double *fragility)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t r = 0; r < R; ++r) {
+        REAL o[3] = { ray_o[3 * r], ray_o[3 * r + 1], ray_o[3 * r + 2] };
+        REAL d[3] = { ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2] };
+        REAL maxt = ray_maxt ? ray_maxt[r] : REAL_MAX;
+        REAL Y[16];
+        if (pr->integrator == ORC_RF && sc->sh_floats) sh_eval(d, sc->sh_degree, Y);
+        REAL beta = R_(1), L[3] = { R_(0), R_(0), R_(0) };
+        uint32_t depth = 0;
+        double tglob = 0.0;
+        double frag[3] = { 1e300, 1e300, 1e300 };
+        int active = 1;
+        if (hit_ids) for (int k = 0; k < cap; ++k) hit_ids[r * cap + k] = -1;
+        /* volprim_rf.py:186: the depth test runs at the END of an iteration, so max_depth == 0
+         * still performs one interaction; reproduced literally. */
+        while (active) {
+            hit_rec h;
+            closest_hit(sc, pr, o, d, maxt, &h);
+            if (h.second_t < REAL_MAX && (double)h.second_t - (double)h.t < frag[0] && h.id >= 0)
+                frag[0] = (double)h.second_t - (double)h.t;
+            if ((double)h.min_abs_t < frag[1]) frag[1] = (double)h.min_abs_t;
+            if ((double)h.min_abs_discr < frag[2]) frag[2] = (double)h.min_abs_discr;
+            if (h.id < 0) {
+                if (pr->integrator == ORC_TOMO && !(depth == 0 && pr->hide_emitters))
+                    for (int ch = 0; ch < 3; ++ch) L[ch] += beta * (REAL)pr->env[ch]; /* tomo:105-111 */
+                break;
+            }
+            if (pr->integrator == ORC_RF) {
+                rf_hit q;
+                rf_interact(sc, pr, h.id, o, d, Y, beta, &q);
+                for (int ch = 0; ch < 3; ++ch) L[ch] = L[ch] + q.Le[ch]; /* rf:145 */
+                beta = beta * q.T;                                       /* rf:146 */
+            } else {
+                beta = beta * tomo_interact(sc, pr, h.id, o, d, NULL, NULL); /* tomo:85 */
+            }
+            if (hit_ids && (int32_t)depth < cap) hit_ids[r * cap + depth] = (int32_t)h.id;
+            if (hit_t && (int32_t)depth < cap) hit_t[r * cap + depth] = tglob + (double)h.t;
+            tglob += (double)h.t + pr->eps_advance;
+            /* ray.o = si.p + ray.d * 1e-4 with si.p = ray(t)          rf:149 / tomo:114 */
+            for (int a = 0; a < 3; ++a) {
+                REAL p = FMA(d[a], h.t, o[a]);
+                o[a] = FMA(d[a], (REAL)pr->eps_advance, p);
+            }
+            depth += 1;                                                  /* rf:170 */
+            if (pr->integrator == ORC_RF && !(beta > (REAL)pr->t_cutoff)) active = 0; /* rf:173-174 */
+            if (!(depth < pr->max_depth)) active = 0;                    /* rf:186 / tomo:125 */
+        }
+        if (pr->integrator == ORC_RF && pr->srgb_primitives)
+            for (int ch = 0; ch < 3; ++ch) L[ch] = srgb_to_linear(L[ch]); /* rf:189-190 */
+        if (rgb) for (int ch = 0; ch < 3; ++ch) rgb[3 * r + ch] = L[ch];
+        if (beta_out) beta_out[r] = beta;
+        if (nhits) nhits[r] = depth;
+        if (fragility) for (int k = 0; k < 3; ++k) fragility[3 * r + k] = frag[k];
+    }
+}
+
+static void chain_dR_to_quat(const ellipsoid *e, double dR[3][3], double g10[10])
+{
+    double x = e->q[0], y = e->q[1], z = e->q[2], w4 = e->q[3];
+    g10[6] += 2 * (y * dR[0][1] + z * dR[0][2] + y * dR[1][0] - 2 * x * dR[1][1] - w4 * dR[1][2] + z * dR[2][0]
+                   + w4 * dR[2][1] - 2 * x * dR[2][2]);
+    g10[7] += 2 * (-2 * y * dR[0][0] + x * dR[0][1] + w4 * dR[0][2] + x * dR[1][0] + z * dR[1][2] - w4 * dR[2][0]
+                   + z * dR[2][1] - 2 * y * dR[2][2]);
+    g10[8] += 2 * (-2 * z * dR[0][0] - w4 * dR[0][1] + x * dR[0][2] + w4 * dR[1][0] - 2 * z * dR[1][1] + y * dR[1][2]
+                   + x * dR[2][0] + y * dR[2][1]);
+    g10[9] += 2 * (-z * dR[0][1] + y * dR[0][2] + z * dR[1][0] - x * dR[1][2] - y * dR[2][0] + x * dR[2][1]);
+}
+
+/* chain d(q)/d(params) for q = sum_i (R^T v)_i^2 / (k s_i)^2, v = p - c (p fixed).  SURVEY Appendix B. */
+static void chain_quadratic(const ellipsoid *e, const REAL p[3], REAL k, REAL dq, double g10[10])
+{
+    REAL v[3] = { p[0] - e->c[0], p[1] - e->c[1], p[2] - e->c[2] }, w[3];
+    rot_t_mul(e->R, v, w);
+    double dw[3], ds[3];
+    for (int i = 0; i < 3; ++i) {
+        double ks = (double)k * e->s[i];
+        dw[i] = 2.0 * w[i] / (ks * ks) * dq;
+        ds[i] = -2.0 * (double)w[i] * w[i] / (ks * ks * e->s[i]) * dq;
+    }
+    /* w_b = sum_a R_ab v_a */
+    double dv[3], dR[3][3];
+    for (int a = 0; a < 3; ++a) {
+        dv[a] = e->R[a][0] * dw[0] + e->R[a][1] * dw[1] + e->R[a][2] * dw[2];
+        for (int b = 0; b < 3; ++b) dR[a][b] = (double)v[a] * dw[b];
+    }
+    for (int a = 0; a < 3; ++a) { g10[a] += -dv[a]; g10[3 + a] += ds[a]; }
+    chain_dR_to_quat(e, dR, g10);
+}
+
+/* d(rho)/d(params) for the full-range line integrals, scaled by drho.  Derived from the closed forms
+ * rho_gauss = exp(-h/2) / (2 pi S sqrt(A)),  rho_epan = (15/(8 pi S)) |w| 2 sqrt((E^2-h)/A) (1 - E^2/3 - 2h/3)
+ * with A = sum w_i^2/s_i^2, B = sum p_i w_i/s_i^2, C = sum p_i^2/s_i^2, h = C - B^2/A, S = sx sy sz,
+ * w = R^T d, p = R^T (o - c)  (equal to common.py:199-206 / :293-315). */
+static void chain_density(const ellipsoid *e, int kernel, const REAL o[3], const REAL d[3], double rho, double drho,
+                          double g10[10])
+{
+    double v[3] = { (double)o[0] - e->c[0], (double)o[1] - e->c[1], (double)o[2] - e->c[2] };
+    double w[3], p[3], s[3] = { e->s[0], e->s[1], e->s[2] };
+    for (int i = 0; i < 3; ++i) {
+        w[i] = e->R[0][i] * (double)d[0] + e->R[1][i] * (double)d[1] + e->R[2][i] * (double)d[2];
+        p[i] = e->R[0][i] * v[0] + e->R[1][i] * v[1] + e->R[2][i] * v[2];
+    }
+    double A = 0, B = 0, C = 0;
+    for (int i = 0; i < 3; ++i) {
+        A += w[i] * w[i] / (s[i] * s[i]);
+        B += p[i] * w[i] / (s[i] * s[i]);
+        C += p[i] * p[i] / (s[i] * s[i]);
+    }
+    double h = C - B * B / A;
+    /* dlnrho = ch * dh + cA * dA/A + cS * dlnS + cW * dln|w| */
+    double ch, cA, cS = -1.0, cW;
+    if (kernel == ORC_GAUSS) { ch = -0.5; cA = -0.5; cW = 0.0; }
+    else {
+        double E2 = (double)e->extent * e->extent;
+        double poly = 1.0 - E2 / 3.0 - 2.0 * h / 3.0;
+        ch = -0.5 / (E2 - h) + (-2.0 / 3.0) / poly;
+        cA = -0.5;
+        cW = 1.0;
+    }
+    double dp[3], dw[3], ds[3];
+    double wn2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    for (int i = 0; i < 3; ++i) {
+        double si2 = s[i] * s[i], si3 = si2 * s[i];
+        double u = p[i] - (B / A) * w[i];
+        /* dh/dp_i = 2u/s^2 ; dh/dw_i = -2 (B/A) u / s^2 ; dh/ds_i = -2 u^2 / s^3 */
+        /* dA/dw_i = 2 w_i / s^2 ; dA/ds_i = -2 w_i^2 / s^3 */
+        dp[i] = ch * (2 * u / si2);
+        dw[i] = ch * (-2 * (B / A) * u / si2) + cA * (2 * w[i] / si2) / A + cW * w[i] / wn2;
+        ds[i] = ch * (-2 * u * u / si3) + cA * (-2 * w[i] * w[i] / si3) / A + cS / s[i];
+    }
+    double scale = rho * drho;
+    double dR[3][3];
+    for (int a = 0; a < 3; ++a) {
+        double dva = e->R[a][0] * dp[0] + e->R[a][1] * dp[1] + e->R[a][2] * dp[2];
+        g10[a] += -dva * scale;
+        g10[3 + a] += ds[a] * scale;
+        for (int b = 0; b < 3; ++b) dR[a][b] = (v[a] * dp[b] + (double)d[a] * dw[b]) * scale;
+    }
+    chain_dR_to_quat(e, dR, g10);
+}
+
+/*
+ * Adjoint loop (PRB), reference_exact semantics.  volprim_rf.py:106-165,
+ * volprim_tomography.py:57-101.  The same closest-hit sequence is replayed.
+ * Gradients are accumulated in double into g_data [n*10], g_attr [n], g_sh [n*C] (caller-zeroed).
+ * `state_in` is used as given (the caller decides between reference_exact and corrected, Q3).
+ */
+EXPORT void orc_trace_adjoint(const orc_scene *sc, const orc_params *pr, int64_t R, const REAL *ray_o,
+                              const REAL *ray_d, const REAL *ray_maxt, const REAL *dL, const REAL *state_in,
+                              double *g_data, double *g_attr, double *g_sh)
+{
+    /* serial over rays: deterministic accumulation order (the oracle is not the thing timed here) */
+    for (int64_t r = 0; r < R; ++r) {
+        REAL o[3] = { ray_o[3 * r], ray_o[3 * r + 1], ray_o[3 * r + 2] };
+        REAL d[3] = { ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2] };
+        REAL maxt = ray_maxt ? ray_maxt[r] : REAL_MAX;
+        REAL g[3] = { dL[3 * r], dL[3 * r + 1], dL[3 * r + 2] };
+        if (g[0] == R_(0) && g[1] == R_(0) && g[2] == R_(0)) continue; /* rf:111-112 */
+        REAL L[3] = { state_in[3 * r], state_in[3 * r + 1], state_in[3 * r + 2] };
+        REAL Y[16];
+        if (pr->integrator == ORC_RF && sc->sh_floats) sh_eval(d, sc->sh_degree, Y);
+        REAL beta = R_(1);
+        uint32_t depth = 0;
+        int active = 1;
+        while (active) {
+            hit_rec h;
+            closest_hit(sc, pr, o, d, maxt, &h);
+            if (h.id < 0) break;
+            int64_t j = h.id;
+            ellipsoid e;
+            gather(sc, j, &e);
+            if (pr->integrator == ORC_RF) {
+                rf_hit q;
+                rf_interact(sc, pr, j, o, d, Y, beta, &q);
+                for (int ch = 0; ch < 3; ++ch) L[ch] = L[ch] - q.Le[ch]; /* rf:145 (adjoint) */
+                /* Lo = Le + L * T / detach(T); zero where non-finite       rf:156-160 */
+                double dalpha = 0.0;
+                for (int ch = 0; ch < 3; ++ch) {
+                    REAL lo = q.Le[ch] + L[ch] * q.T / q.T;
+                    if (!isfinite((double)lo)) continue;
+                    /* d/d(1-T) of Le, and d/dT of L*T/detach(T) */
+                    if (q.le_finite[ch]) {
+                        dalpha += (double)g[ch] * (double)beta * q.col[ch];
+                        if (q.colraw[ch] > R_(0) && sc->sh_floats) {
+                            double dcol = (double)g[ch] * (double)beta * q.one_minus_T;
+                            int nb = sc->sh_floats / 3;
+                            for (int i = 0; i < nb; ++i) g_sh[j * sc->sh_floats + 3 * i + ch] += (double)Y[i] * dcol;
+                        }
+                    }
+                    dalpha -= (double)g[ch] * (double)L[ch] / (double)q.T;
+                }
+                REAL araw = sc->attr[j] * q.G;
+                if (araw < R_(0.9999)) { /* min() passes the gradient to its first argument */
+                    g_attr[j] += dalpha * (double)q.G;
+                    double dG = dalpha * (double)sc->attr[j];
+                    if (pr->kernel == ORC_GAUSS) {
+                        double dq = -0.5 * (double)q.G * dG;
+                        double tmp[10] = { 0 };
+                        chain_quadratic(&e, q.ppeak, R_(1), R_(1), tmp);
+                        for (int k = 0; k < 10; ++k) g_data[j * 10 + k] += tmp[k] * dq;
+                    } else if (q.G > R_(0)) {
+                        double dq = -0.75 * dG;
+                        double tmp[10] = { 0 };
+                        chain_quadratic(&e, q.ppeak, R_(3), R_(1), tmp);
+                        for (int k = 0; k < 10; ++k) g_data[j * 10 + k] += tmp[k] * dq;
+                    }
+                }
+                beta = beta * q.T;
+            } else {
+                REAL rho, raw;
+                REAL T = tomo_interact(sc, pr, j, o, d, &rho, &raw);
+                beta = beta * T;
+                double dT = 0.0;
+                for (int ch = 0; ch < 3; ++ch) {
+                    REAL lo = L[ch] * T / T; /* tomo:92-96 */
+                    if (!isfinite((double)lo)) continue;
+                    dT += (double)g[ch] * (double)L[ch] / (double)T;
+                }
+                g_attr[j] += -(double)rho * (double)T * dT;
+                if (rho > R_(0) && isfinite((double)raw)) {
+                    double drho = -(double)sc->attr[j] * (double)T * dT;
+                    chain_density(&e, pr->kernel, o, d, (double)rho, drho, g_data + j * 10);
+                }
+            }
+            for (int a = 0; a < 3; ++a) {
+                REAL p = FMA(d[a], h.t, o[a]);
+                o[a] = FMA(d[a], (REAL)pr->eps_advance, p);
+            }
+            depth += 1;
+            if (pr->integrator == ORC_RF && !(beta > (REAL)pr->t_cutoff)) active = 0;
+            if (!(depth < pr->max_depth)) active = 0;
+        }
+    }
+}
+
+/* ---- scalar entry points for the known-answer / golden tests ---- */
+static void make_ellipsoid(const REAL rec10[10], REAL extent, ellipsoid *e)
+{
+    for (int i = 0; i < 3; ++i) { e->c[i] = rec10[i]; e->s[i] = rec10[3 + i]; }
+    for (int i = 0; i < 4; ++i) e->q[i] = rec10[6 + i];
+    quat_to_matrix(e->q, e->R);
+    e->extent = extent;
+}
+EXPORT void orc_quat_to_matrix(const REAL q[4], REAL out9[9])
+{
+    REAL R[3][3];
+    quat_to_matrix(q, R);
+    memcpy(out9, R, sizeof R);
+}
+EXPORT void orc_sh_eval(const REAL d[3], int degree, REAL *Y) { sh_eval(d, degree, Y); }
+EXPORT REAL orc_srgb_to_linear(REAL x) { return srgb_to_linear(x); }
+EXPORT REAL orc_srgb_to_linear_deriv(REAL x) { return srgb_to_linear_deriv(x); }
+EXPORT int orc_ray_ellipsoid(const REAL o[3], const REAL d[3], const REAL rec10[10], REAL extent, REAL *tn, REAL *tf)
+{
+    ellipsoid e;
+    make_ellipsoid(rec10, extent, &e);
+    *tn = *tf = R_(0);
+    return ray_ellipsoid(o, d, &e, tn, tf, NULL);
+}
+EXPORT REAL orc_kernel_eval(int kernel, const REAL p[3], const REAL rec10[10])
+{
+    ellipsoid e;
+    make_ellipsoid(rec10, R_(3), &e);
+    return kernel == ORC_GAUSS ? gaussian_eval(p, &e) : epanechnikov_eval(p, &e);
+}
+EXPORT REAL orc_density_integral(int kernel, const REAL o[3], const REAL d[3], const REAL rec10[10], REAL extent)
+{
+    ellipsoid e;
+    make_ellipsoid(rec10, extent, &e);
+    return kernel == ORC_GAUSS ? gaussian_density_integral(o, d, &e, NULL)
+                               : epanechnikov_density_integral(o, d, &e, NULL);
+}
+EXPORT REAL orc_rf_transmission(int kernel, const REAL o[3], const REAL d[3], const REAL rec10[10], REAL opacity)
+{
+    ellipsoid e;
+    make_ellipsoid(rec10, R_(3), &e);
+    return rf_transmission(o, d, &e, opacity, kernel, NULL, NULL);
+}
+EXPORT int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+EXPORT void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
