@@ -252,17 +252,21 @@ static REAL gaussian_density_integral(const REAL o[3], const REAL d[3], const el
     REAL v[3] = { o[0] - e->c[0], o[1] - e->c[1], o[2] - e->c[2] }, w[3], p[3];
     rot_t_mul(e->R, d, w);
     rot_t_mul(e->R, v, p);
+    /* fp32 note: this expression cancels catastrophically when |o - c| >> s (terms ~ (|p|/s)^2 against a
+     * result of O(1)); the reference evaluates it in Float all the same.  The association order below is the
+     * literal Python expression (left to right); the CUDA kernel mirrors it operation by operation. */
     REAL sx2 = e->s[0] * e->s[0], sy2 = e->s[1] * e->s[1], sz2 = e->s[2] * e->s[2];
     REAL wx2 = w[0] * w[0], wy2 = w[1] * w[1], wz2 = w[2] * w[2];
     REAL px2 = p[0] * p[0], py2 = p[1] * p[1], pz2 = p[2] * p[2];
-    REAL C1 = (sx2 * sy2 * wz2 + sx2 * sz2 * wy2) + sy2 * sz2 * wx2;
-    REAL num = ((((px2 * sy2 + py2 * sx2) * wz2
-                  - R_(2) * p[2] * w[2] * (p[1] * sx2 * w[1] + p[0] * sy2 * w[0]))
-                 + wy2 * (px2 * sz2 + pz2 * sx2))
-                - R_(2) * p[0] * p[1] * sz2 * w[0] * w[1])
-               + wx2 * (py2 * sz2 + pz2 * sy2);
+    REAL C1 = ((sx2 * sy2) * wz2 + (sx2 * sz2) * wy2) + (sy2 * sz2) * wx2;
+    REAL t1 = (px2 * sy2 + py2 * sx2) * wz2;
+    REAL t2 = ((R_(2) * p[2]) * w[2]) * ((p[1] * sx2) * w[1] + (p[0] * sy2) * w[0]);
+    REAL t3 = wy2 * (px2 * sz2 + pz2 * sx2);
+    REAL t4 = ((((R_(2) * p[0]) * p[1]) * sz2) * w[0]) * w[1];
+    REAL t5 = wx2 * (py2 * sz2 + pz2 * sy2);
+    REAL num = (((t1 - t2) + t3) - t4) + t5;
     REAL exponent = num / (R_(2) * C1);
-    REAL denom = R_(2) * R_(PI_D) * SQRT(C1);
+    REAL denom = (R_(2) * R_(PI_D)) * SQRT(C1);
     REAL density = EXP(-exponent) / denom;
     if (raw) *raw = density;
     if (!(density > R_(0))) density = R_(0);       /* dr.maximum(density, 0); NaN -> 0 below */

@@ -1,0 +1,223 @@
+// vp_api.cu -- extern "C" surface of libvolprim_cuda.so (declared in include/volprim_cuda.h).
+#include "vp_internal.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+
+namespace {
+std::string g_create_error;
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+void free_buf(DevBuffer &b)
+{
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.cap = 0;
+}
+}  // namespace
+
+int vp_fail(vp_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+int vp_ensure(vp_ctx *ctx, DevBuffer &b, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return VP_OK;
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8;  // slack so that slowly growing clouds do not reallocate every step
+    cudaError_t e = cudaMalloc(&b.ptr, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&b.ptr, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b.ptr = nullptr;
+        return vp_fail(ctx, VP_E_OOM, std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return VP_OK;
+}
+
+DevScene vp_dev_scene(const vp_ctx *ctx)
+{
+    DevScene S;
+    S.n = (int32_t)ctx->n;
+    S.sh_floats = ctx->sh_floats;
+    // sh_degree = int(sqrt(C // 3 - 1))   (reference volprim_rf.py:89, reproduced literally)
+    S.sh_degree = ctx->sh_floats > 0 ? (int)std::sqrt((double)(ctx->sh_floats / 3 - 1)) : -1;
+    if (ctx->sh_floats > 0 && 3 * (S.sh_degree + 1) * (S.sh_degree + 1) != ctx->sh_floats) S.sh_degree = 99;  // rejected by dispatch
+    S.sh_stride4 = (ctx->sh_floats + 3) / 4;
+    S.extent = ctx->extent;
+    S.root = ctx->root;
+    S.geo0 = (const float4 *)ctx->geo0.ptr;
+    S.geo1 = (const float4 *)ctx->geo1.ptr;
+    S.geo2 = (const float4 *)ctx->geo2.ptr;
+    S.sh4 = (const float4 *)ctx->sh4.ptr;
+    S.nodes = (const float4 *)ctx->nodes.ptr;
+    S.perm = (const int32_t *)ctx->perm.ptr;
+    S.inv_perm = (const int32_t *)ctx->inv_perm.ptr;
+    return S;
+}
+
+extern "C" {
+
+int vp_version(void) { return VP_VERSION; }
+
+int vp_create(int device, vp_ctx **out)
+{
+    if (!out) return vp_fail(nullptr, VP_E_INVALID, "vp_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return vp_fail(nullptr, VP_E_CUDA, std::string("vp_create: no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return vp_fail(nullptr, VP_E_INVALID, "vp_create: device index out of range");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return vp_fail(nullptr, VP_E_CUDA, std::string("vp_create: ") + cudaGetErrorString(e));
+    if (prop.major != 10)
+        return vp_fail(nullptr, VP_E_CUDA, std::string("vp_create: libvolprim_cuda.so is built for sm_100a only; device is sm_") +
+                                               std::to_string(prop.major) + std::to_string(prop.minor));
+    vp_ctx *ctx = new (std::nothrow) vp_ctx();
+    if (!ctx) return vp_fail(nullptr, VP_E_OOM, "vp_create: out of host memory");
+    ctx->device = device;
+    *out = ctx;
+    return VP_OK;
+}
+
+int vp_destroy(vp_ctx *ctx)
+{
+    if (!ctx) return VP_OK;
+    DeviceGuard g(ctx->device);
+    DevBuffer *all[] = { &ctx->raw_data, &ctx->raw_attr, &ctx->raw_sh, &ctx->geo0, &ctx->geo1, &ctx->geo2, &ctx->sh4,
+                         &ctx->nodes, &ctx->perm, &ctx->inv_perm, &ctx->leaf_lo, &ctx->leaf_hi, &ctx->keys[0],
+                         &ctx->keys[1], &ctx->vals[0], &ctx->vals[1], &ctx->hist, &ctx->parent, &ctx->counters,
+                         &ctx->bounds, &ctx->stats };
+    for (DevBuffer *b : all) free_buf(*b);
+    delete ctx;
+    return VP_OK;
+}
+
+const char *vp_last_error(const vp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int vp_set_primitives(vp_ctx *ctx, int64_t n, const float *data10, const float *attr, const float *sh,
+                      int32_t sh_floats, float extent, void *stream)
+{
+    if (!ctx) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < 0) return vp_fail(ctx, VP_E_INVALID, "vp_set_primitives: negative primitive count");
+    if (n > 0 && !data10) return vp_fail(ctx, VP_E_INVALID, "vp_set_primitives: data10 is NULL");
+    if (sh && sh_floats <= 0) return vp_fail(ctx, VP_E_INVALID, "vp_set_primitives: sh given but sh_floats <= 0");
+    if (!(extent > 0.f)) return vp_fail(ctx, VP_E_INVALID, "vp_set_primitives: extent must be > 0");
+    if (!sh) sh_floats = 0;
+    int rc;
+    if ((rc = vp_ensure(ctx, ctx->raw_data, sizeof(float) * 10 * (size_t)n))) return rc;
+    if ((rc = vp_ensure(ctx, ctx->raw_attr, sizeof(float) * (size_t)n))) return rc;
+    if ((rc = vp_ensure(ctx, ctx->raw_sh, sizeof(float) * (size_t)n * (size_t)sh_floats))) return rc;
+    if (n > 0) {
+        VP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->raw_data.ptr, data10, sizeof(float) * 10 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        if (attr) VP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->raw_attr.ptr, attr, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        if (sh_floats)
+            VP_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->raw_sh.ptr, sh, sizeof(float) * (size_t)n * sh_floats, cudaMemcpyDeviceToDevice, st));
+    }
+    ctx->have_attr = attr != nullptr;
+    if (ctx->n != n || ctx->sh_floats != sh_floats) ctx->built = false;
+    ctx->n = n;
+    ctx->sh_floats = sh_floats;
+    ctx->extent = extent;
+    ctx->have_prims = true;
+    return VP_OK;
+}
+
+int vp_build(vp_ctx *ctx, void *stream)
+{
+    if (!ctx) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    return vp_build_impl(ctx, false, (cudaStream_t)stream);
+}
+
+int vp_refit(vp_ctx *ctx, void *stream)
+{
+    if (!ctx) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    return vp_build_impl(ctx, true, (cudaStream_t)stream);
+}
+
+int vp_trace_forward(vp_ctx *ctx, const vp_params *params, int64_t n_rays, const float *ray_o, const float *ray_d,
+                     const float *ray_maxt, float *out_rgb, float *out_T, uint32_t *out_nhits, int32_t *out_hit_ids,
+                     int32_t id_cap, int64_t id_ray_stride, int64_t id_hit_stride, void *stream)
+{
+    if (!ctx) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    return vp_trace_forward_impl(ctx, params, n_rays, ray_o, ray_d, ray_maxt, out_rgb, out_T, out_nhits, out_hit_ids,
+                                 id_cap, id_ray_stride, id_hit_stride, (cudaStream_t)stream);
+}
+
+int vp_trace_adjoint(vp_ctx *ctx, const vp_params *params, int64_t n_rays, const float *ray_o, const float *ray_d,
+                     const float *ray_maxt, const float *d_L, const float *state_in, const int32_t *hit_ids,
+                     const uint32_t *hit_counts, int32_t id_cap, int64_t id_ray_stride, int64_t id_hit_stride,
+                     float *g_data10, float *g_attr, float *g_sh, void *stream)
+{
+    if (!ctx) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    return vp_trace_adjoint_impl(ctx, params, n_rays, ray_o, ray_d, ray_maxt, d_L, state_in, hit_ids, hit_counts, id_cap,
+                                 id_ray_stride, id_hit_stride, g_data10, g_attr, g_sh, (cudaStream_t)stream);
+}
+
+int vp_raygen_perspective(vp_ctx *ctx, const vp_camera *cam, int32_t spp, const float *jitter, float *ray_o,
+                          float *ray_d, float *ray_maxt, void *stream)
+{
+    if (!ctx) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    return vp_raygen_impl(ctx, cam, spp, jitter, ray_o, ray_d, ray_maxt, (cudaStream_t)stream);
+}
+
+int vp_get_stats(vp_ctx *ctx, vp_stats *host_out, void *stream)
+{
+    if (!ctx || !host_out) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    std::memset(host_out, 0, sizeof *host_out);
+    if (!ctx->stats.ptr) return VP_OK;
+    VP_CUDA_CHECK(ctx, cudaMemcpyAsync(host_out, ctx->stats.ptr, sizeof *host_out, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    VP_CUDA_CHECK(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return VP_OK;
+}
+
+int vp_debug_bvh(vp_ctx *ctx, float *out_nodes, int32_t *out_perm, int64_t *n_internal, void *stream)
+{
+    if (!ctx) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    if (!ctx->built) return vp_fail(ctx, VP_E_STATE, "vp_debug_bvh: not built");
+    int64_t ni = ctx->n > 1 ? ctx->n - 1 : 0;
+    if (n_internal) *n_internal = ni;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_nodes && ni > 0)
+        VP_CUDA_CHECK(ctx, cudaMemcpyAsync(out_nodes, ctx->nodes.ptr, sizeof(float) * 16 * (size_t)ni, cudaMemcpyDeviceToDevice, st));
+    if (out_perm && ctx->n > 0)
+        VP_CUDA_CHECK(ctx, cudaMemcpyAsync(out_perm, ctx->perm.ptr, sizeof(int32_t) * (size_t)ctx->n, cudaMemcpyDeviceToDevice, st));
+    return VP_OK;
+}
+
+}  // extern "C"

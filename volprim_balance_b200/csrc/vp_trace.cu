@@ -1,0 +1,846 @@
+// vp_trace.cu -- per-ray volumetric-primitive integration on sm_100a.
+//
+// Replaces the Dr.Jit megakernels "Primitive splatting (Primal/Backward)" and "Primitive tracing
+// (Primal/Backward)" together with the scene.ray_intersect() they call once per hit
+// (reference: volprim/integrators/volprim_rf.py:103-192, volprim_tomography.py:47-127).
+//
+// Algorithm (one thread per ray, rays walked in 8x4 pixel tiles per warp):
+//   pass:   ordered stack traversal of the LBVH from the ray's CURRENT origin, keeping the K closest
+//           front-face entries (t > 0) in a register-resident, sorted k-buffer;
+//   drain:  for each buffered entry in order, the entry distance is RE-EVALUATED against the current,
+//           re-based origin with the same fixed-order fp32 arithmetic as the parity oracle.  This applies
+//           the reference's "advance the origin by 1e-4 and query again with back-face culling" rule
+//           exactly (entries that fell behind the advanced origin are dropped) and keeps
+//           the origin bit-identical to the one the reference loop would carry;
+//   refill: when a full buffer has been drained and the ray is still alive, the next pass starts from
+//           the current origin.  The ray stops on miss, max_depth, or (rf) beta <= t_cutoff.
+// The adjoint either replays recorded hit lists (no BVH access) or re-traces like the primal.
+#include "vp_internal.cuh"
+
+#include <cfloat>
+#include <cmath>
+
+namespace {
+
+constexpr int KBUF = 16;       // k-buffer entries per ray
+constexpr int STACK_MAX = 96;  // LBVH depth bound: 63 Morton bits + index tie-break bits
+constexpr int TRACE_THREADS = 128;
+constexpr int NODE_SENTINEL = 0x7fffffff;
+#define VP_INF __int_as_float(0x7f800000)
+
+struct Isect {
+    bool valid;
+    float tn, tf;
+    float3 ro, rd;  // R^T (o - c), R^T d  (fixed evaluation order)
+};
+
+// ray_ellipsoid_intersection (reference common.py:346-367, RT-Gems-2 branch) followed by
+// mi.math.improved_solve_quadratic.  Individually rounded operations: must match oracle/volprim_oracle.c
+// ray_ellipsoid() bit for bit, because these distances order the hits and drive the epsilon cull.
+__device__ __forceinline__ Isect exact_isect(float3 o, float3 d, float4 g0, float4 g1, const Mat3 &R, float extent)
+{
+    Isect r;
+    float3 sc = make_float3(__fmul_rn(g1.x, extent), __fmul_rn(g1.y, extent), __fmul_rn(g1.z, extent));
+    float3 v = make_float3(__fsub_rn(o.x, g0.x), __fsub_rn(o.y, g0.y), __fsub_rn(o.z, g0.z));
+    r.rd = vp_rot_t_mul_rn(R, d);
+    r.ro = vp_rot_t_mul_rn(R, v);
+    float3 dd = make_float3(__fdiv_rn(r.rd.x, sc.x), __fdiv_rn(r.rd.y, sc.y), __fdiv_rn(r.rd.z, sc.z));
+    float3 oo = make_float3(__fdiv_rn(r.ro.x, sc.x), __fdiv_rn(r.ro.y, sc.y), __fdiv_rn(r.ro.z, sc.z));
+    float a = vp_dot_rn(dd, dd);
+    float b = -vp_dot_rn(oo, dd);
+    float c = __fsub_rn(vp_dot_rn(oo, oo), 1.f);
+    float ba = __fdiv_rn(b, a);
+    float3 l = make_float3(__fadd_rn(oo.x, __fmul_rn(ba, dd.x)), __fadd_rn(oo.y, __fmul_rn(ba, dd.y)),
+                           __fadd_rn(oo.z, __fmul_rn(ba, dd.z)));
+    float discr = __fsub_rn(1.f, vp_dot_rn(l, l));
+    r.valid = false;
+    r.tn = r.tf = 0.f;
+    if (!(discr >= 0.f) || a == 0.f) return r;
+    float sq = __fsqrt_rn(__fmul_rn(a, discr));
+    float q = __fadd_rn(b, copysignf(sq, b));
+    float x0 = __fdiv_rn(c, q);
+    float x1 = __fdiv_rn(q, a);
+    r.tn = fminf(x0, x1);
+    r.tf = fmaxf(x0, x1);
+    r.valid = isfinite(x0) && isfinite(x1);
+    return r;
+}
+
+struct Counters {
+    uint32_t hits, candidates, nodes, passes, overflow;
+};
+
+// sorted insertion into the register k-buffer (ascending t; ties keep the lower sorted position first)
+__device__ __forceinline__ void kbuf_insert(float (&bt)[KBUF], int (&bi)[KBUF], float t, int id)
+{
+#pragma unroll
+    for (int i = 0; i < KBUF; ++i) {
+        bool sw = (t < bt[i]) || (t == bt[i] && id < bi[i]);
+        float tt = sw ? bt[i] : t;
+        int ti = sw ? bi[i] : id;
+        bt[i] = sw ? t : bt[i];
+        bi[i] = sw ? id : bi[i];
+        t = tt;
+        id = ti;
+    }
+}
+
+__device__ __forceinline__ void leaf_test(const DevScene &S, int pos, float3 o, float3 d, float (&bt)[KBUF],
+                                          int (&bi)[KBUF], Counters &cn)
+{
+    float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
+    Mat3 R = vp_quat_to_matrix_rn(g2);
+    Isect is = exact_isect(o, d, g0, g1, R, S.extent);
+    cn.candidates++;
+    // front face in front of the origin; back faces are culled (RayFlags.BackfaceCulling, rf:127)
+    if (is.valid && is.tn > 0.f && (is.tn < bt[KBUF - 1] || (is.tn == bt[KBUF - 1] && pos < bi[KBUF - 1])))
+        kbuf_insert(bt, bi, is.tn, pos);
+}
+
+__device__ __forceinline__ bool slab(float3 lo, float3 hi, float3 o, float3 inv, float tlim, float &t0)
+{
+    float ax = (lo.x - o.x) * inv.x, bx = (hi.x - o.x) * inv.x;
+    float ay = (lo.y - o.y) * inv.y, by = (hi.y - o.y) * inv.y;
+    float az = (lo.z - o.z) * inv.z, bz = (hi.z - o.z) * inv.z;
+    t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+    float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tlim));
+    // boxes are padded at build time; widen the exit by a few ulp for the reciprocal's rounding
+    return t0 <= t1 * 1.0000005f;
+}
+
+// One k-buffer pass: the K closest front-face entries seen from origin o.
+__device__ __forceinline__ void fill_pass(const DevScene &S, float3 o, float3 d, float (&bt)[KBUF], int (&bi)[KBUF],
+                                       Counters &cn)
+{
+#pragma unroll
+    for (int i = 0; i < KBUF; ++i) { bt[i] = VP_INF; bi[i] = -1; }
+    cn.passes++;
+    if (S.n <= 0) return;
+    if (S.root < 0) { leaf_test(S, ~S.root, o, d, bt, bi, cn); return; }
+    float3 inv;
+    inv.x = 1.f / (fabsf(d.x) > 1e-30f ? d.x : copysignf(1e-30f, d.x));
+    inv.y = 1.f / (fabsf(d.y) > 1e-30f ? d.y : copysignf(1e-30f, d.y));
+    inv.z = 1.f / (fabsf(d.z) > 1e-30f ? d.z : copysignf(1e-30f, d.z));
+    int stack_n[STACK_MAX];
+    float stack_t[STACK_MAX];
+    int sp = 0;
+    int node = S.root;
+    while (node != NODE_SENTINEL) {
+        if (node >= 0) {
+            const float4 *nd = S.nodes + 4ll * node;
+            float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+            cn.nodes++;
+            float tlim = bt[KBUF - 1];
+            float tl, tr;
+            bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), o, inv, tlim, tl);
+            bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), o, inv, tlim, tr);
+            int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
+            if (hl && hr) {
+                bool lfirst = tl <= tr;
+                int far_n = lfirst ? right : left;
+                float far_t = lfirst ? tr : tl;
+                node = lfirst ? left : right;
+                if (sp < STACK_MAX) { stack_n[sp] = far_n; stack_t[sp] = far_t; ++sp; }
+                else cn.overflow++;
+                continue;
+            }
+            if (hl) { node = left; continue; }
+            if (hr) { node = right; continue; }
+        } else {
+            leaf_test(S, ~node, o, d, bt, bi, cn);
+        }
+        // pop, skipping subtrees that the tightened k-th distance has culled meanwhile
+        node = NODE_SENTINEL;
+        while (sp > 0) {
+            --sp;
+            if (stack_t[sp] <= bt[KBUF - 1]) { node = stack_n[sp]; break; }
+        }
+    }
+}
+
+// ---- closed-form primitive evaluation --------------------------------------------------------
+
+template <int D>
+__device__ __forceinline__ void sh_basis(float3 d, float (&Y)[(D + 1) * (D + 1)])
+{
+    // dr.sh_eval: Sloan's real-SH recurrences with Condon-Shortley sign, index l(l+1)+m (rf:90)
+    float x = d.x, y = d.y, z = d.z;
+    Y[0] = 0.28209479177387814f;
+    if constexpr (D >= 1) {
+        Y[2] = 0.48860251190291992f * z;
+        Y[3] = -0.48860251190291992f * x;
+        Y[1] = -0.48860251190291992f * y;
+    }
+    if constexpr (D >= 2) {
+        float z2 = z * z;
+        Y[6] = 0.94617469575756008f * z2 - 0.31539156525251999f;
+        float tb = -1.0925484305920792f * z;
+        Y[7] = tb * x;
+        Y[5] = tb * y;
+        float c1 = x * x - y * y, s1 = 2.f * x * y;
+        Y[8] = 0.54627421529603959f * c1;
+        Y[4] = 0.54627421529603959f * s1;
+        if constexpr (D >= 3) {
+            Y[12] = z * (1.8658816629505769f * z2 - 1.1195289977703462f);
+            float tc = -2.2852289973223288f * z2 + 0.45704579946446572f;
+            Y[13] = tc * x;
+            Y[11] = tc * y;
+            float td = 1.4453057213202769f * z;
+            Y[14] = td * c1;
+            Y[10] = td * s1;
+            float c2 = x * c1 - y * s1, s2 = x * s1 + y * c1;
+            Y[15] = -0.59004358992664352f * c2;
+            Y[9] = -0.59004358992664352f * s2;
+        }
+    }
+}
+
+// eval_sh_emission (rf:82-100): raw = sum_i Y_i f_i + 0.5 ; col = max(raw, 0).  128-bit loads of the
+// primitive's contiguous coefficient block.
+template <int D>
+__device__ __forceinline__ void sh_color(const DevScene &S, int pos, const float (&Y)[(D + 1) * (D + 1)], float (&raw)[3])
+{
+    constexpr int NB = (D + 1) * (D + 1);
+    constexpr int C = 3 * NB;
+    constexpr int N4 = (C + 3) / 4;
+    const float4 *f = S.sh4 + (size_t)pos * N4;
+    float acc[3] = { 0.f, 0.f, 0.f };
+    float4 v[N4];
+#pragma unroll
+    for (int k = 0; k < N4; ++k) v[k] = __ldg(f + k);
+#pragma unroll
+    for (int k = 0; k < N4; ++k) {
+        const float e[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int idx = 4 * k + c;
+            if (idx < C) acc[idx % 3] = fmaf(Y[idx / 3], e[c], acc[idx % 3]);
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) raw[ch] = acc[ch] + 0.5f;
+}
+
+struct RfEval {
+    float T, G, op;
+    float3 pp;  // p_peak
+};
+
+// eval_transmission (rf:63-80) with GaussianKernel.eval / EpanechnikovKernel.eval (common.py:153-159, 251-259)
+template <int KERNEL>
+__device__ __forceinline__ RfEval rf_eval(float3 o, float3 d, float4 g0, float4 g1, const Mat3 &R, const Isect &is)
+{
+    RfEval e;
+    float3 oo = make_float3(is.ro.x / g1.x, is.ro.y / g1.y, is.ro.z / g1.z);
+    float3 dd = make_float3(is.rd.x / g1.x, is.rd.y / g1.y, is.rd.z / g1.z);
+    float od = vp_dot_rn(oo, dd), dd2 = vp_dot_rn(dd, dd);
+    float tp = -od / dd2;
+    e.pp = make_float3(fmaf(d.x, tp, o.x), fmaf(d.y, tp, o.y), fmaf(d.z, tp, o.z));
+    float3 v = make_float3(e.pp.x - g0.x, e.pp.y - g0.y, e.pp.z - g0.z);
+    float3 w = vp_rot_t_mul_rn(R, v);
+    if (KERNEL == VP_KERNEL_GAUSSIAN) {
+        float q = (w.x * w.x) / (g1.x * g1.x) + (w.y * w.y) / (g1.y * g1.y) + (w.z * w.z) / (g1.z * g1.z);
+        e.G = expf(-0.5f * q);
+    } else {
+        float ux = w.x / (g1.x * 3.f), uy = w.y / (g1.y * 3.f), uz = w.z / (g1.z * 3.f);
+        float dist = sqrtf(ux * ux + uy * uy + uz * uz);
+        e.G = fmaxf(0.75f * (1.f - dist * dist), 0.f);
+    }
+    e.op = g0.w;
+    float a = e.op * e.G;
+    if (!(a < 0.9999f)) a = 0.9999f;
+    e.T = 1.f - a;
+    return e;
+}
+
+// GaussianKernel.density_integral full range (common.py:199-206, 238-243); returns clamped rho
+__device__ __forceinline__ float gauss_density_integral(float4 g1, const Isect &is)
+{
+    float3 w = is.rd, p = is.ro;
+    // The literal expression cancels catastrophically in fp32 when |o - c| >> s; it is therefore evaluated
+    // with individually rounded operations in exactly the oracle's association order (bit-identical inputs
+    // to exp), instead of letting the compiler contract it differently from the CPU restatement.
+    float sx2 = __fmul_rn(g1.x, g1.x), sy2 = __fmul_rn(g1.y, g1.y), sz2 = __fmul_rn(g1.z, g1.z);
+    float wx2 = __fmul_rn(w.x, w.x), wy2 = __fmul_rn(w.y, w.y), wz2 = __fmul_rn(w.z, w.z);
+    float px2 = __fmul_rn(p.x, p.x), py2 = __fmul_rn(p.y, p.y), pz2 = __fmul_rn(p.z, p.z);
+    float C1 = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(sx2, sy2), wz2), __fmul_rn(__fmul_rn(sx2, sz2), wy2)),
+                         __fmul_rn(__fmul_rn(sy2, sz2), wx2));
+    float t1 = __fmul_rn(__fadd_rn(__fmul_rn(px2, sy2), __fmul_rn(py2, sx2)), wz2);
+    float t2 = __fmul_rn(__fmul_rn(__fmul_rn(2.f, p.z), w.z),
+                         __fadd_rn(__fmul_rn(__fmul_rn(p.y, sx2), w.y), __fmul_rn(__fmul_rn(p.x, sy2), w.x)));
+    float t3 = __fmul_rn(wy2, __fadd_rn(__fmul_rn(px2, sz2), __fmul_rn(pz2, sx2)));
+    float t4 = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(2.f, p.x), p.y), sz2), w.x), w.y);
+    float t5 = __fmul_rn(wx2, __fadd_rn(__fmul_rn(py2, sz2), __fmul_rn(pz2, sy2)));
+    float num = __fadd_rn(__fsub_rn(__fadd_rn(__fsub_rn(t1, t2), t3), t4), t5);
+    float exponent = __fdiv_rn(num, __fmul_rn(2.f, C1));
+    float denom = __fmul_rn(6.2831855f, __fsqrt_rn(C1));
+    float density = __fdiv_rn(expf(-exponent), denom);
+    if (!(density > 0.f) || !isfinite(density)) density = 0.f;
+    return density;
+}
+
+// EpanechnikovKernel.density_integral full range (common.py:287-324); bandwidth s over the extent*s chord
+__device__ __forceinline__ float epan_density_integral(float3 o, float3 d, float4 g0, float4 g1, const Mat3 &R,
+                                                       const Isect &is)
+{
+    if (!is.valid || !(is.tn < is.tf) || !(is.tf > 0.f)) return 0.f;
+    float3 a0 = make_float3(fmaf(d.x, is.tn, o.x) - g0.x, fmaf(d.y, is.tn, o.y) - g0.y, fmaf(d.z, is.tn, o.z) - g0.z);
+    float3 a1 = make_float3(fmaf(d.x, is.tf, o.x) - g0.x, fmaf(d.y, is.tf, o.y) - g0.y, fmaf(d.z, is.tf, o.z) - g0.z);
+    float3 p = vp_rot_t_mul_rn(R, a0), p1 = vp_rot_t_mul_rn(R, a1);
+    float3 w = make_float3(p1.x - p.x, p1.y - p.y, p1.z - p.z);
+    float t = sqrtf(w.x * w.x + w.y * w.y + w.z * w.z);
+    w.x /= t; w.y /= t; w.z /= t;
+    float sx2 = g1.x * g1.x, sy2 = g1.y * g1.y, sz2 = g1.z * g1.z;
+    float t2 = t * t, t3 = t2 * t;
+    float poly = sx2 * sy2 * t3 * (w.z * w.z) + 3.f * p.z * sx2 * sy2 * t2 * w.z + sx2 * sz2 * t3 * (w.y * w.y)
+               + 3.f * p.y * sx2 * sz2 * t2 * w.y + sy2 * sz2 * t3 * (w.x * w.x) + 3.f * p.x * sy2 * sz2 * t2 * w.x
+               + (((3.f * (p.x * p.x) - 3.f * sx2) * sy2 + 3.f * (p.y * p.y) * sx2) * sz2
+                  + 3.f * (p.z * p.z) * sx2 * sy2) * t;
+    float s3 = (g1.x * g1.x * g1.x) * (g1.y * g1.y * g1.y) * (g1.z * g1.z * g1.z);
+    float density = -poly * 5.f / (8.f * 3.14159265358979f * s3);
+    if (!(density > 0.f) || !isfinite(density)) density = 0.f;
+    return density;
+}
+
+__device__ __forceinline__ float srgb_to_linear(float x)
+{
+    return x <= 0.04045f ? x / 12.92f : powf((x + 0.055f) / 1.055f, 2.4f);
+}
+
+// thread -> ray index; with an image hint the 32 lanes of a warp cover an 8x4 pixel tile
+__device__ __forceinline__ int64_t ray_index(int64_t t, int W, int H)
+{
+    if (W <= 0) return t;
+    int64_t per = (int64_t)W * H;
+    int64_t img = t / per;
+    int rem = (int)(t - img * per);
+    int tile = rem >> 5, lane = rem & 31;
+    int tiles_x = W >> 3;
+    int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    int x = tx * 8 + (lane & 7), y = ty * 4 + (lane >> 3);
+    return img * per + (int64_t)y * W + x;
+}
+
+__device__ __forceinline__ void flush_counters(const Counters &cn, vp_stats *st)
+{
+    if (!st) return;
+    uint32_t v[5] = { cn.hits, cn.candidates, cn.nodes, cn.passes, cn.overflow };
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        for (int off = 16; off; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd((unsigned long long *)&st->hits, (unsigned long long)v[0]);
+        atomicAdd((unsigned long long *)&st->candidates, (unsigned long long)v[1]);
+        atomicAdd((unsigned long long *)&st->node_visits, (unsigned long long)v[2]);
+        atomicAdd((unsigned long long *)&st->passes, (unsigned long long)v[3]);
+        if (v[4]) atomicAdd((unsigned long long *)&st->stack_overflows, (unsigned long long)v[4]);
+    }
+}
+
+struct TraceArgs {
+    int64_t R;
+    const float *o, *d, *maxt;
+    float *rgb, *T;
+    uint32_t *nhits;
+    int32_t *ids;
+    int32_t cap;
+    int64_t rs, hs;
+    // adjoint
+    const float *dL, *state_in;
+    const int32_t *rec_ids;
+    const uint32_t *rec_counts;
+    float *g_data, *g_attr, *g_sh;
+    vp_stats *stats;
+};
+
+// ---- forward ----------------------------------------------------------------------------------
+template <int INTEG, int KERNEL, int D>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_forward(DevScene S, vp_params P, TraceArgs A)
+{
+    int64_t t = (int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x;
+    Counters cn = { 0, 0, 0, 0, 0 };
+    if (t < A.R) {
+        const int64_t r = ray_index(t, P.image_width, P.image_height);
+        float3 o = make_float3(A.o[3 * r], A.o[3 * r + 1], A.o[3 * r + 2]);
+        const float3 d = make_float3(A.d[3 * r], A.d[3 * r + 1], A.d[3 * r + 2]);
+        const float maxt = A.maxt ? A.maxt[r] : FLT_MAX;
+        float beta = 1.f, L[3] = { 0.f, 0.f, 0.f };
+        uint32_t depth = 0;
+        bool missed = false, alive = true;
+        float bt[KBUF];
+        int bi[KBUF];
+        while (alive) {
+            fill_pass(S, o, d, bt, bi, cn);
+            const bool full = bt[KBUF - 1] < VP_INF;
+            constexpr int NY = (D >= 0) ? (D + 1) * (D + 1) : 1;
+            float Y[NY];
+            if constexpr (INTEG == VP_INTEGRATOR_RF && D >= 0) sh_basis<(D >= 0 ? D : 0)>(d, Y);
+#pragma unroll 1
+            while (bt[0] < VP_INF) {
+                const int pos = bi[0];
+#pragma unroll
+                for (int i = 0; i < KBUF - 1; ++i) { bt[i] = bt[i + 1]; bi[i] = bi[i + 1]; }
+                bt[KBUF - 1] = VP_INF;
+                float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
+                Mat3 Rm = vp_quat_to_matrix_rn(g2);
+                Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
+                if (!is.valid || !(is.tn > 0.f)) continue;      // entry fell behind the advanced origin (Q1)
+                if (!(is.tn <= maxt)) { missed = true; alive = false; break; }
+                float T;
+                if constexpr (INTEG == VP_INTEGRATOR_RF) {
+                    RfEval e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
+                    T = e.T;
+                    float raw[3] = { 0.f, 0.f, 0.f };
+                    if constexpr (D >= 0) sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw);
+                    const float omt = 1.f - T;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        float col = (D >= 0) ? fmaxf(raw[ch], 0.f) : 0.f;
+                        float le = beta * omt * col;           // rf:140
+                        if (!isfinite(le)) le = 0.f;            // rf:141
+                        L[ch] += le;                            // rf:145
+                    }
+                } else {
+                    float rho = (KERNEL == VP_KERNEL_GAUSSIAN) ? gauss_density_integral(g1, is)
+                                                               : epan_density_integral(o, d, g0, g1, Rm, is);
+                    T = expf(-rho * g0.w);                      // tomo:44
+                }
+                beta *= T;                                      // rf:146 / tomo:85
+                if (A.ids && depth < (uint32_t)A.cap) A.ids[r * A.rs + depth * A.hs] = __float_as_int(g1.w);
+                // ray.o = si.p + ray.d * 1e-4                     rf:149 / tomo:114
+                o.x = fmaf(d.x, P.eps_advance, fmaf(d.x, is.tn, o.x));
+                o.y = fmaf(d.y, P.eps_advance, fmaf(d.y, is.tn, o.y));
+                o.z = fmaf(d.z, P.eps_advance, fmaf(d.z, is.tn, o.z));
+                depth += 1;
+                cn.hits++;
+                if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) { alive = false; break; }  // rf:173-174
+                if (!(depth < P.max_depth)) { alive = false; break; }                             // rf:186
+            }
+            if (alive && !full) { missed = true; alive = false; }
+        }
+        if (INTEG == VP_INTEGRATOR_TOMO && missed && !(depth == 0 && P.hide_emitters)) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) L[ch] += beta * P.env[ch];   // tomo:105-111
+        }
+        if (INTEG == VP_INTEGRATOR_RF && P.srgb_primitives) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) L[ch] = srgb_to_linear(L[ch]);  // rf:189-190
+        }
+        A.rgb[3 * r] = L[0];
+        A.rgb[3 * r + 1] = L[1];
+        A.rgb[3 * r + 2] = L[2];
+        if (A.T) A.T[r] = beta;
+        if (A.nhits) A.nhits[r] = depth;
+        if (A.ids)
+            for (uint32_t k = depth; k < (uint32_t)A.cap; ++k) A.ids[r * A.rs + k * A.hs] = -1;
+    }
+    flush_counters(cn, A.stats);
+}
+
+// ---- adjoint ----------------------------------------------------------------------------------
+
+// chain d(loss)/dR (3x3) to the un-normalised quaternion (x, y, z, w)
+__device__ __forceinline__ void chain_dR_to_quat(float4 q, const float (&dR)[3][3], float (&gq)[4])
+{
+    float x = q.x, y = q.y, z = q.z, w = q.w;
+    gq[0] = 2.f * (y * dR[0][1] + z * dR[0][2] + y * dR[1][0] - 2.f * x * dR[1][1] - w * dR[1][2] + z * dR[2][0]
+                   + w * dR[2][1] - 2.f * x * dR[2][2]);
+    gq[1] = 2.f * (-2.f * y * dR[0][0] + x * dR[0][1] + w * dR[0][2] + x * dR[1][0] + z * dR[1][2] - w * dR[2][0]
+                   + z * dR[2][1] - 2.f * y * dR[2][2]);
+    gq[2] = 2.f * (-2.f * z * dR[0][0] - w * dR[0][1] + x * dR[0][2] + w * dR[1][0] - 2.f * z * dR[1][1] + y * dR[1][2]
+                   + x * dR[2][0] + y * dR[2][1]);
+    gq[3] = 2.f * (-z * dR[0][1] + y * dR[0][2] + z * dR[1][0] - x * dR[1][2] - y * dR[2][0] + x * dR[2][1]);
+}
+
+__device__ __forceinline__ void scatter_geo(float *g_data, int orig, const float (&g10)[10])
+{
+    // [N*10] records are 8-byte aligned: five 64-bit vector reductions
+    float2 *dst = reinterpret_cast<float2 *>(g_data + 10ll * orig);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) atomicAdd(dst + k, make_float2(g10[2 * k], g10[2 * k + 1]));
+}
+
+// one rf interaction of the adjoint; returns T
+template <int KERNEL, int D>
+__device__ __forceinline__ float rf_adjoint_hit(const DevScene &S, const TraceArgs &A, int pos, float3 o, float3 d,
+                                                float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is,
+                                                float beta, const float (&g)[3], float (&L)[3],
+                                                const float (&Y)[(D >= 0) ? (D + 1) * (D + 1) : 1])
+{
+    constexpr int NB = (D >= 0) ? (D + 1) * (D + 1) : 0;
+    const int orig = __float_as_int(g1.w);
+    RfEval e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
+    float raw[3] = { 0.f, 0.f, 0.f };
+    if constexpr (D >= 0) sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw);
+    const float omt = 1.f - e.T;
+    float dalpha = 0.f, dcol[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float col = (D >= 0) ? fmaxf(raw[ch], 0.f) : 0.f;
+        float le = beta * omt * col;
+        bool lef = isfinite(le);
+        if (!lef) le = 0.f;
+        L[ch] -= le;                                  // rf:145 (adjoint branch)
+        float lo = le + L[ch] * e.T / e.T;            // rf:156-159
+        dcol[ch] = 0.f;
+        if (isfinite(lo)) {                           // rf:160
+            if (lef) {
+                dalpha += g[ch] * beta * col;
+                if (raw[ch] > 0.f) dcol[ch] = g[ch] * beta * omt;
+            }
+            dalpha -= g[ch] * L[ch] / e.T;
+        }
+    }
+    if constexpr (D >= 0) {
+        if (A.g_sh && (dcol[0] != 0.f || dcol[1] != 0.f || dcol[2] != 0.f)) {
+            constexpr int C = 3 * NB;
+            float *dst = A.g_sh + (size_t)orig * C;
+            if constexpr (C % 4 == 0) {
+#pragma unroll
+                for (int k = 0; k < C / 4; ++k) {
+                    float4 v;
+                    v.x = Y[(4 * k + 0) / 3] * dcol[(4 * k + 0) % 3];
+                    v.y = Y[(4 * k + 1) / 3] * dcol[(4 * k + 1) % 3];
+                    v.z = Y[(4 * k + 2) / 3] * dcol[(4 * k + 2) % 3];
+                    v.w = Y[(4 * k + 3) / 3] * dcol[(4 * k + 3) % 3];
+                    atomicAdd(reinterpret_cast<float4 *>(dst) + k, v);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < C; ++k) atomicAdd(dst + k, Y[k / 3] * dcol[k % 3]);
+            }
+        }
+    }
+    if (e.op * e.G < 0.9999f) {                       // dr.minimum passes the gradient to opacity * density
+        atomicAdd(A.g_attr + orig, dalpha * e.G);
+        float dG = dalpha * e.op;
+        float dq = 0.f;
+        float k2 = 1.f;
+        if (KERNEL == VP_KERNEL_GAUSSIAN) dq = -0.5f * e.G * dG;
+        else { dq = (e.G > 0.f) ? -0.75f * dG : 0.f; k2 = 9.f; }
+        if (dq != 0.f) {
+            // q = sum_i w_i^2 / (k s_i)^2, w = R^T v, v = p_peak - c ; dq/dt_peak = 0 at the peak
+            float3 v = make_float3(e.pp.x - g0.x, e.pp.y - g0.y, e.pp.z - g0.z);
+            float3 w = vp_rot_t_mul_rn(Rm, v);
+            float sx2 = k2 * g1.x * g1.x, sy2 = k2 * g1.y * g1.y, sz2 = k2 * g1.z * g1.z;
+            float dw[3] = { 2.f * w.x / sx2 * dq, 2.f * w.y / sy2 * dq, 2.f * w.z / sz2 * dq };
+            float g10[10];
+            g10[3] = -w.x * dw[0] / g1.x;
+            g10[4] = -w.y * dw[1] / g1.y;
+            g10[5] = -w.z * dw[2] / g1.z;
+            const float va[3] = { v.x, v.y, v.z };
+            float dR[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                g10[a] = -(Rm.m[a][0] * dw[0] + Rm.m[a][1] * dw[1] + Rm.m[a][2] * dw[2]);
+#pragma unroll
+                for (int b = 0; b < 3; ++b) dR[a][b] = va[a] * dw[b];
+            }
+            float gq[4];
+            chain_dR_to_quat(g2, dR, gq);
+            g10[6] = gq[0]; g10[7] = gq[1]; g10[8] = gq[2]; g10[9] = gq[3];
+            scatter_geo(A.g_data, orig, g10);
+        }
+    }
+    return e.T;
+}
+
+// one tomography interaction of the adjoint; returns T.  L stays state_in until the ray escapes (tomo:92-101).
+template <int KERNEL>
+__device__ __forceinline__ float tomo_adjoint_hit(const DevScene &S, const TraceArgs &A, float3 o, float3 d, float4 g0,
+                                                  float4 g1, float4 g2, const Mat3 &Rm, const Isect &is,
+                                                  const float (&g)[3], const float (&L)[3])
+{
+    const int orig = __float_as_int(g1.w);
+    float rho = (KERNEL == VP_KERNEL_GAUSSIAN) ? gauss_density_integral(g1, is)
+                                               : epan_density_integral(o, d, g0, g1, Rm, is);
+    float sigma = g0.w;
+    float T = expf(-rho * sigma);
+    float dT = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float lo = L[ch] * T / T;
+        if (isfinite(lo)) dT += g[ch] * L[ch] / T;
+    }
+    atomicAdd(A.g_attr + orig, -rho * T * dT);
+    if (rho > 0.f) {
+        float drho = -sigma * T * dT;
+        // closed forms (see oracle chain_density / DESIGN.md): A = sum w^2/s^2, B = sum p w/s^2, C = sum p^2/s^2,
+        // h = C - B^2/A.  h and u = p - (B/A) w do not change when the origin slides along the ray, so they are
+        // evaluated from the ENTRY point (|p| <= extent * s) where fp32 does not cancel; B/A is shifted back.
+        float3 w = is.rd;
+        float3 ae = make_float3(fmaf(d.x, is.tn, o.x) - g0.x, fmaf(d.y, is.tn, o.y) - g0.y, fmaf(d.z, is.tn, o.z) - g0.z);
+        float3 p = vp_rot_t_mul_rn(Rm, ae);
+        float s[3] = { g1.x, g1.y, g1.z }, wv[3] = { w.x, w.y, w.z }, pv[3] = { p.x, p.y, p.z };
+        float Aq = 0.f, Be = 0.f, Cq = 0.f, wn2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float is2 = 1.f / (s[i] * s[i]);
+            Aq += wv[i] * wv[i] * is2;
+            Be += pv[i] * wv[i] * is2;
+            Cq += pv[i] * pv[i] * is2;
+            wn2 += wv[i] * wv[i];
+        }
+        const float BAe = Be / Aq;        // B/A seen from the entry point
+        const float BA = BAe - is.tn;     // B/A seen from the current origin
+        float h = Cq - Be * BAe;
+        float ch_, cW;
+        if (KERNEL == VP_KERNEL_GAUSSIAN) { ch_ = -0.5f; cW = 0.f; }
+        else {
+            float E2 = S.extent * S.extent;
+            ch_ = -0.5f / (E2 - h) + (-2.f / 3.f) / (1.f - E2 / 3.f - 2.f * h / 3.f);
+            cW = 1.f;
+        }
+        float scale = rho * drho;
+        float dp[3], dw[3], g10[10];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float si2 = s[i] * s[i], si3 = si2 * s[i];
+            float u = pv[i] - BAe * wv[i];
+            dp[i] = ch_ * (2.f * u / si2);
+            dw[i] = ch_ * (-2.f * BA * u / si2) - (wv[i] / si2) / Aq + cW * wv[i] / wn2;
+            g10[3 + i] = (ch_ * (-2.f * u * u / si3) + (wv[i] * wv[i] / si3) / Aq - 1.f / s[i]) * scale;
+        }
+        const float va[3] = { o.x - g0.x, o.y - g0.y, o.z - g0.z }, da[3] = { d.x, d.y, d.z };
+        float dR[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            g10[a] = -(Rm.m[a][0] * dp[0] + Rm.m[a][1] * dp[1] + Rm.m[a][2] * dp[2]) * scale;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) dR[a][b] = (va[a] * dp[b] + da[a] * dw[b]) * scale;
+        }
+        float gq[4];
+        chain_dR_to_quat(g2, dR, gq);
+        g10[6] = gq[0]; g10[7] = gq[1]; g10[8] = gq[2]; g10[9] = gq[3];
+        scatter_geo(A.g_data, orig, g10);
+    }
+    return T;
+}
+
+template <int INTEG, int KERNEL, int D, bool REPLAY>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_adjoint(DevScene S, vp_params P, TraceArgs A)
+{
+    int64_t t = (int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x;
+    Counters cn = { 0, 0, 0, 0, 0 };
+    if (t < A.R) {
+        const int64_t r = ray_index(t, P.image_width, P.image_height);
+        const float g[3] = { A.dL[3 * r], A.dL[3 * r + 1], A.dL[3 * r + 2] };
+        if (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f) {   // rf:111-112
+            float3 o = make_float3(A.o[3 * r], A.o[3 * r + 1], A.o[3 * r + 2]);
+            const float3 d = make_float3(A.d[3 * r], A.d[3 * r + 1], A.d[3 * r + 2]);
+            const float maxt = A.maxt ? A.maxt[r] : FLT_MAX;
+            float L[3] = { A.state_in[3 * r], A.state_in[3 * r + 1], A.state_in[3 * r + 2] };
+            float beta = 1.f;
+            uint32_t depth = 0;
+            constexpr int NY = (D >= 0) ? (D + 1) * (D + 1) : 1;
+            float Y[NY];
+            if constexpr (INTEG == VP_INTEGRATOR_RF && D >= 0) sh_basis<(D >= 0 ? D : 0)>(d, Y);
+            else Y[0] = 0.f;
+
+            auto interact = [&](int pos, float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is) {
+                float T;
+                if constexpr (INTEG == VP_INTEGRATOR_RF)
+                    T = rf_adjoint_hit<KERNEL, D>(S, A, pos, o, d, g0, g1, g2, Rm, is, beta, g, L, Y);
+                else
+                    T = tomo_adjoint_hit<KERNEL>(S, A, o, d, g0, g1, g2, Rm, is, g, L);
+                beta *= T;
+                o.x = fmaf(d.x, P.eps_advance, fmaf(d.x, is.tn, o.x));
+                o.y = fmaf(d.y, P.eps_advance, fmaf(d.y, is.tn, o.y));
+                o.z = fmaf(d.z, P.eps_advance, fmaf(d.z, is.tn, o.z));
+                depth += 1;
+                cn.hits++;
+            };
+
+            if constexpr (REPLAY) {
+                uint32_t n = A.rec_counts[r];
+                if (n > (uint32_t)A.cap) n = (uint32_t)A.cap;
+                for (uint32_t k = 0; k < n; ++k) {
+                    int orig = A.rec_ids[r * A.rs + k * A.hs];
+                    if (orig < 0) break;
+                    int pos = __ldg(S.inv_perm + orig);
+                    float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
+                    Mat3 Rm = vp_quat_to_matrix_rn(g2);
+                    Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
+                    interact(pos, g0, g1, g2, Rm, is);
+                }
+            } else {
+                bool alive = true;
+                float bt[KBUF];
+                int bi[KBUF];
+                while (alive) {
+                    fill_pass(S, o, d, bt, bi, cn);
+                    const bool full = bt[KBUF - 1] < VP_INF;
+#pragma unroll 1
+                    while (bt[0] < VP_INF) {
+                        const int pos = bi[0];
+#pragma unroll
+                        for (int i = 0; i < KBUF - 1; ++i) { bt[i] = bt[i + 1]; bi[i] = bi[i + 1]; }
+                        bt[KBUF - 1] = VP_INF;
+                        float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
+                        Mat3 Rm = vp_quat_to_matrix_rn(g2);
+                        Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
+                        if (!is.valid || !(is.tn > 0.f)) continue;
+                        if (!(is.tn <= maxt)) { alive = false; break; }
+                        interact(pos, g0, g1, g2, Rm, is);
+                        if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) { alive = false; break; }
+                        if (!(depth < P.max_depth)) { alive = false; break; }
+                    }
+                    if (alive && !full) alive = false;
+                }
+            }
+        }
+    }
+    flush_counters(cn, A.stats);
+}
+
+__global__ void k_raygen(vp_camera cam, int spp, const float *__restrict__ jitter, float *__restrict__ ro,
+                         float *__restrict__ rd, float *__restrict__ rmaxt)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)cam.width * cam.height * spp;
+    if (i >= total) return;
+    int64_t pix = i / spp;
+    int x = (int)(pix % cam.width), y = (int)(pix / cam.width);
+    float jx = jitter ? jitter[2 * i] : 0.5f, jy = jitter ? jitter[2 * i + 1] : 0.5f;
+    float u = ((float)x + jx) / (float)cam.width, v = ((float)y + jy) / (float)cam.height;
+    float tan_half = tanf(cam.fov_x_deg * 0.5f * 0.017453292519943295f);
+    float aspect = (float)cam.width / (float)cam.height;
+    // Mitsuba perspective sensor: +z forward, +x to the LEFT of the image, +y up
+    float lx = (1.f - 2.f * u + 2.f * cam.cx) * tan_half;
+    float ly = (1.f - 2.f * v + 2.f * cam.cy) * tan_half / aspect;
+    float inv_n = rsqrtf(lx * lx + ly * ly + 1.f);
+    float3 dl = make_float3(lx * inv_n, ly * inv_n, inv_n);
+    const float *m = cam.to_world;
+    float3 dw = make_float3(m[0] * dl.x + m[1] * dl.y + m[2] * dl.z, m[4] * dl.x + m[5] * dl.y + m[6] * dl.z,
+                            m[8] * dl.x + m[9] * dl.y + m[10] * dl.z);
+    float inv_z = 1.f / dl.z;
+    float near_t = cam.near_clip * inv_z, far_t = cam.far_clip * inv_z;
+    ro[3 * i] = fmaf(dw.x, near_t, m[3]);
+    ro[3 * i + 1] = fmaf(dw.y, near_t, m[7]);
+    ro[3 * i + 2] = fmaf(dw.z, near_t, m[11]);
+    rd[3 * i] = dw.x;
+    rd[3 * i + 1] = dw.y;
+    rd[3 * i + 2] = dw.z;
+    if (rmaxt) rmaxt[i] = far_t - near_t;
+}
+
+template <int INTEG, int KERNEL, int D>
+void launch_forward(const DevScene &S, const vp_params &P, const TraceArgs &A, cudaStream_t st)
+{
+    int64_t blocks = (A.R + TRACE_THREADS - 1) / TRACE_THREADS;
+    k_trace_forward<INTEG, KERNEL, D><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
+}
+
+template <int INTEG, int KERNEL, int D>
+void launch_adjoint(const DevScene &S, const vp_params &P, const TraceArgs &A, cudaStream_t st)
+{
+    int64_t blocks = (A.R + TRACE_THREADS - 1) / TRACE_THREADS;
+    if (A.rec_ids) k_trace_adjoint<INTEG, KERNEL, D, true><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
+    else k_trace_adjoint<INTEG, KERNEL, D, false><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
+}
+
+template <bool FWD>
+int dispatch(vp_ctx *ctx, const DevScene &S, const vp_params &P, const TraceArgs &A, cudaStream_t st)
+{
+#define VP_LAUNCH(I, K, D)                                   \
+    do {                                                     \
+        if (FWD) launch_forward<I, K, D>(S, P, A, st);       \
+        else launch_adjoint<I, K, D>(S, P, A, st);           \
+        return VP_OK;                                        \
+    } while (0)
+    const bool gauss = P.kernel == VP_KERNEL_GAUSSIAN;
+    if (P.integrator == VP_INTEGRATOR_TOMO) {
+        if (gauss) VP_LAUNCH(VP_INTEGRATOR_TOMO, VP_KERNEL_GAUSSIAN, -1);
+        VP_LAUNCH(VP_INTEGRATOR_TOMO, VP_KERNEL_EPANECHNIKOV, -1);
+    }
+    switch (S.sh_degree) {
+    case -1: if (gauss) VP_LAUNCH(VP_INTEGRATOR_RF, VP_KERNEL_GAUSSIAN, -1); VP_LAUNCH(VP_INTEGRATOR_RF, VP_KERNEL_EPANECHNIKOV, -1);
+    case 0: if (gauss) VP_LAUNCH(VP_INTEGRATOR_RF, VP_KERNEL_GAUSSIAN, 0); VP_LAUNCH(VP_INTEGRATOR_RF, VP_KERNEL_EPANECHNIKOV, 0);
+    case 1: if (gauss) VP_LAUNCH(VP_INTEGRATOR_RF, VP_KERNEL_GAUSSIAN, 1); VP_LAUNCH(VP_INTEGRATOR_RF, VP_KERNEL_EPANECHNIKOV, 1);
+    case 2: if (gauss) VP_LAUNCH(VP_INTEGRATOR_RF, VP_KERNEL_GAUSSIAN, 2); VP_LAUNCH(VP_INTEGRATOR_RF, VP_KERNEL_EPANECHNIKOV, 2);
+    case 3: if (gauss) VP_LAUNCH(VP_INTEGRATOR_RF, VP_KERNEL_GAUSSIAN, 3); VP_LAUNCH(VP_INTEGRATOR_RF, VP_KERNEL_EPANECHNIKOV, 3);
+    default: break;
+    }
+#undef VP_LAUNCH
+    return vp_fail(ctx, VP_E_INVALID, "sh_coeffs: only SH degrees 0..3 (3, 12, 27 or 48 floats per primitive) are supported");
+}
+
+int check_common(vp_ctx *ctx, const vp_params *p, int64_t R, const char *who)
+{
+    if (!p) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": params is NULL");
+    if (!ctx->built) return vp_fail(ctx, VP_E_STATE, std::string(who) + ": acceleration structure not built (call vp_build)");
+    if (p->integrator != VP_INTEGRATOR_RF && p->integrator != VP_INTEGRATOR_TOMO)
+        return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": unknown integrator");
+    if (p->kernel != VP_KERNEL_GAUSSIAN && p->kernel != VP_KERNEL_EPANECHNIKOV)
+        return vp_fail(ctx, VP_E_INVALID, "Unknown kernel type! Should be one of \"gaussian\" or \"epanechnikov\".");
+    if (R < 0 || R > 0x7fffffffll * TRACE_THREADS) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": bad ray count");
+    if (p->image_width > 0) {
+        if (p->image_width % 8 || p->image_height % 4 || p->image_height <= 0 ||
+            R % ((int64_t)p->image_width * p->image_height))
+            return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": image hint needs width % 8 == 0, height % 4 == 0 and "
+                                                                 "a ray count that is a multiple of width*height");
+    }
+    return VP_OK;
+}
+
+}  // namespace
+
+int vp_trace_forward_impl(vp_ctx *ctx, const vp_params *p, int64_t R, const float *o, const float *d, const float *maxt,
+                          float *rgb, float *T, uint32_t *nhits, int32_t *ids, int32_t cap, int64_t rs, int64_t hs,
+                          cudaStream_t st)
+{
+    int rc = check_common(ctx, p, R, "vp_trace_forward");
+    if (rc) return rc;
+    if (R == 0) return VP_OK;
+    if (!o || !d || !rgb) return vp_fail(ctx, VP_E_INVALID, "vp_trace_forward: ray_o, ray_d and out_rgb are required");
+    if (ids && cap <= 0) return vp_fail(ctx, VP_E_INVALID, "vp_trace_forward: out_hit_ids needs id_cap > 0");
+    if ((rc = vp_ensure(ctx, ctx->stats, sizeof(vp_stats)))) return rc;
+    VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->stats.ptr, 0, sizeof(vp_stats), st));
+    DevScene S = vp_dev_scene(ctx);
+    TraceArgs A = {};
+    A.R = R; A.o = o; A.d = d; A.maxt = maxt; A.rgb = rgb; A.T = T; A.nhits = nhits;
+    A.ids = ids; A.cap = ids ? cap : 0; A.rs = rs; A.hs = hs;
+    A.stats = (vp_stats *)ctx->stats.ptr;
+    rc = dispatch<true>(ctx, S, *p, A, st);
+    if (rc) return rc;
+    VP_CUDA_CHECK(ctx, cudaGetLastError());
+    return VP_OK;
+}
+
+int vp_trace_adjoint_impl(vp_ctx *ctx, const vp_params *p, int64_t R, const float *o, const float *d, const float *maxt,
+                          const float *dL, const float *state_in, const int32_t *ids, const uint32_t *counts,
+                          int32_t cap, int64_t rs, int64_t hs, float *g_data, float *g_attr, float *g_sh,
+                          cudaStream_t st)
+{
+    int rc = check_common(ctx, p, R, "vp_trace_adjoint");
+    if (rc) return rc;
+    if (R == 0) return VP_OK;
+    if (!o || !d || !dL || !state_in || !g_data || !g_attr)
+        return vp_fail(ctx, VP_E_INVALID, "vp_trace_adjoint: rays, d_L, state_in, g_data10 and g_attr are required");
+    if (ids && (!counts || cap <= 0)) return vp_fail(ctx, VP_E_INVALID, "vp_trace_adjoint: hit_ids needs hit_counts and id_cap > 0");
+    if (p->integrator == VP_INTEGRATOR_RF && ctx->sh_floats > 0 && !g_sh)
+        return vp_fail(ctx, VP_E_INVALID, "vp_trace_adjoint: g_sh is required when the primitives carry sh_coeffs");
+    if ((rc = vp_ensure(ctx, ctx->stats, sizeof(vp_stats)))) return rc;
+    VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->stats.ptr, 0, sizeof(vp_stats), st));
+    DevScene S = vp_dev_scene(ctx);
+    TraceArgs A = {};
+    A.R = R; A.o = o; A.d = d; A.maxt = maxt; A.dL = dL; A.state_in = state_in;
+    A.rec_ids = ids; A.rec_counts = counts; A.cap = cap; A.rs = rs; A.hs = hs;
+    A.g_data = g_data; A.g_attr = g_attr; A.g_sh = g_sh;
+    A.stats = (vp_stats *)ctx->stats.ptr;
+    rc = dispatch<false>(ctx, S, *p, A, st);
+    if (rc) return rc;
+    VP_CUDA_CHECK(ctx, cudaGetLastError());
+    return VP_OK;
+}
+
+int vp_raygen_impl(vp_ctx *ctx, const vp_camera *cam, int32_t spp, const float *jitter, float *o, float *d, float *maxt,
+                   cudaStream_t st)
+{
+    if (!cam || !o || !d) return vp_fail(ctx, VP_E_INVALID, "vp_raygen_perspective: camera, ray_o and ray_d are required");
+    if (cam->width <= 0 || cam->height <= 0 || spp <= 0) return vp_fail(ctx, VP_E_INVALID, "vp_raygen_perspective: bad film size or spp");
+    int64_t total = (int64_t)cam->width * cam->height * spp;
+    k_raygen<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(*cam, spp, jitter, o, d, maxt);
+    VP_CUDA_CHECK(ctx, cudaGetLastError());
+    return VP_OK;
+}
