@@ -75,6 +75,8 @@ DevScene vp_dev_scene(const vp_ctx *ctx)
     S.geo1 = (const float4 *)ctx->geo1.ptr;
     S.geo2 = (const float4 *)ctx->geo2.ptr;
     S.sh4 = (const float4 *)ctx->sh4.ptr;
+    S.xf = (const float4 *)ctx->xf.ptr;
+    S.info = (const float *)ctx->info.ptr;
     S.nodes = (const float4 *)ctx->nodes.ptr;
     S.perm = (const int32_t *)ctx->perm.ptr;
     S.inv_perm = (const int32_t *)ctx->inv_perm.ptr;
@@ -110,7 +112,7 @@ int vp_destroy(vp_ctx *ctx)
 {
     if (!ctx) return VP_OK;
     DeviceGuard g(ctx->device);
-    DevBuffer *all[] = { &ctx->raw_data, &ctx->raw_attr, &ctx->raw_sh, &ctx->geo0, &ctx->geo1, &ctx->geo2, &ctx->sh4,
+    DevBuffer *all[] = { &ctx->raw_data, &ctx->raw_attr, &ctx->raw_sh, &ctx->geo0, &ctx->geo1, &ctx->geo2, &ctx->sh4, &ctx->xf, &ctx->info,
                          &ctx->nodes, &ctx->perm, &ctx->inv_perm, &ctx->leaf_lo, &ctx->leaf_hi, &ctx->keys[0],
                          &ctx->keys[1], &ctx->vals[0], &ctx->vals[1], &ctx->hist, &ctx->parent, &ctx->counters,
                          &ctx->bounds, &ctx->stats };

@@ -228,11 +228,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint64_t *
 __global__ void k_gather_soa(const float *__restrict__ data10, const float *__restrict__ attr,
                              const float *__restrict__ sh, int n, int sh_floats, int sh_stride4, float extent,
                              const uint32_t *__restrict__ order, float4 *__restrict__ geo0, float4 *__restrict__ geo1,
-                             float4 *__restrict__ geo2, float4 *__restrict__ sh4, int32_t *__restrict__ perm,
+                             float4 *__restrict__ geo2, float4 *__restrict__ sh4, float4 *__restrict__ xf, float *__restrict__ info,
+                             int32_t *__restrict__ perm,
                              int32_t *__restrict__ inv_perm, float4 *__restrict__ leaf_lo, float4 *__restrict__ leaf_hi)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    float area = 0.f;
+    if (p < n) {
     int j = (int)order[p];
     const float *rec = data10 + 10ll * j;
     float c[3] = { rec[0], rec[1], rec[2] }, s[3] = { rec[3], rec[4], rec[5] };
@@ -289,6 +291,47 @@ __global__ void k_gather_soa(const float *__restrict__ data10, const float *__re
     }
     leaf_lo[p] = make_float4(lo[0], lo[1], lo[2], 0.f);
     leaf_hi[p] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    // unit-sphere transform for the ordering test: M = diag(1/(extent s)) R^T (fp32 from the double matrix)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double se = (double)s[i] * (double)extent;
+        xf[3ll * p + i] = make_float4((float)(R[0][i] / se), (float)(R[1][i] / se), (float)(R[2][i] / se), c[i]);
+    }
+    // mean projected area of the leaf box = surface area / 4 (feeds the initial interval width)
+    float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+    if (isfinite(ex) && isfinite(ey) && isfinite(ez) && ex > 0.f && ey > 0.f && ez > 0.f)
+        area = 0.5f * (ex * ey + ey * ez + ez * ex);
+    }
+    for (int off = 16; off; off >>= 1) area += __shfl_xor_sync(0xffffffffu, area, off);
+    if ((threadIdx.x & 31) == 0 && area > 0.f) atomicAdd(info + 7, area);
+}
+
+// scene box (union of the root's child boxes, or the single leaf) and the initial interval width
+// delta0 = 2 TARGET / (box crossings per unit length), crossings = sum(mean projected leaf area) / volume
+__global__ void k_scene_info(int n, const float *__restrict__ nodes, const float4 *__restrict__ leaf_lo,
+                             const float4 *__restrict__ leaf_hi, float *__restrict__ info)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float lo[3], hi[3];
+    if (n == 1) {
+        lo[0] = leaf_lo[0].x; lo[1] = leaf_lo[0].y; lo[2] = leaf_lo[0].z;
+        hi[0] = leaf_hi[0].x; hi[1] = leaf_hi[0].y; hi[2] = leaf_hi[0].z;
+    } else {
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = fminf(nodes[a], nodes[6 + a]);
+            hi[a] = fmaxf(nodes[3 + a], nodes[9 + a]);
+        }
+    }
+    float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+    float diag = sqrtf(ex * ex + ey * ey + ez * ez);
+    float vol = ex * ey * ez;
+    float area = info[7];
+    float delta0 = diag * (1.f / 64.f);
+    if (vol > 0.f && area > 0.f && isfinite(vol) && isfinite(area)) delta0 = 2.f * 12.f * vol / area;
+    if (!(delta0 > 0.f) || !isfinite(delta0)) delta0 = 1.f;
+    delta0 = fminf(delta0, fmaxf(diag, 1e-20f));
+    for (int a = 0; a < 3; ++a) { info[a] = lo[a]; info[3 + a] = hi[a]; }
+    info[6] = delta0;
 }
 
 // 5. Karras 2012
@@ -401,6 +444,8 @@ int vp_build_impl(vp_ctx *ctx, bool refit_only, cudaStream_t st)
     if ((rc = vp_ensure(ctx, ctx->geo1, sizeof(float4) * n))) return rc;
     if ((rc = vp_ensure(ctx, ctx->geo2, sizeof(float4) * n))) return rc;
     if ((rc = vp_ensure(ctx, ctx->sh4, sizeof(float4) * (size_t)n * (sh_stride4 > 0 ? sh_stride4 : 1)))) return rc;
+    if ((rc = vp_ensure(ctx, ctx->xf, sizeof(float4) * 3 * (size_t)n))) return rc;
+    if ((rc = vp_ensure(ctx, ctx->info, sizeof(float) * 8))) return rc;
     if ((rc = vp_ensure(ctx, ctx->nodes, sizeof(float) * 16 * (size_t)(n > 1 ? n - 1 : 1)))) return rc;
     if ((rc = vp_ensure(ctx, ctx->perm, sizeof(int32_t) * n))) return rc;
     if ((rc = vp_ensure(ctx, ctx->inv_perm, sizeof(int32_t) * n))) return rc;
@@ -444,9 +489,11 @@ int vp_build_impl(vp_ctx *ctx, bool refit_only, cudaStream_t st)
         order = (const uint32_t *)ctx->perm.ptr;  // perm holds the same values (int32 >= 0)
     }
 
+    VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->info.ptr, 0, sizeof(float) * 8, st));
     k_gather_soa<<<cdiv(n, B), B, 0, st>>>(data10, attr, sh, n, ctx->sh_floats, sh_stride4, ctx->extent, order,
                                            (float4 *)ctx->geo0.ptr, (float4 *)ctx->geo1.ptr, (float4 *)ctx->geo2.ptr,
-                                           (float4 *)ctx->sh4.ptr, (int32_t *)ctx->perm.ptr,
+                                           (float4 *)ctx->sh4.ptr, (float4 *)ctx->xf.ptr, (float *)ctx->info.ptr,
+                                           (int32_t *)ctx->perm.ptr,
                                            (int32_t *)ctx->inv_perm.ptr, (float4 *)ctx->leaf_lo.ptr,
                                            (float4 *)ctx->leaf_hi.ptr);
     if (n == 1) {
@@ -463,6 +510,8 @@ int vp_build_impl(vp_ctx *ctx, bool refit_only, cudaStream_t st)
                                           (int32_t *)ctx->counters.ptr);
         ctx->root = 0;
     }
+    k_scene_info<<<1, 32, 0, st>>>(n, (const float *)ctx->nodes.ptr, (const float4 *)ctx->leaf_lo.ptr,
+                                   (const float4 *)ctx->leaf_hi.ptr, (float *)ctx->info.ptr);
     VP_CUDA_CHECK(ctx, cudaGetLastError());
     ctx->built = true;
     ctx->built_n = n64;

@@ -4,16 +4,23 @@
 // (Primal/Backward)" together with the scene.ray_intersect() they call once per hit
 // (reference: volprim/integrators/volprim_rf.py:103-192, volprim_tomography.py:47-127).
 //
-// Algorithm (one thread per ray, rays walked in 8x4 pixel tiles per warp):
-//   pass:   ordered stack traversal of the LBVH from the ray's CURRENT origin, keeping the K closest
-//           front-face entries (t > 0) in a register-resident, sorted k-buffer;
-//   drain:  for each buffered entry in order, the entry distance is RE-EVALUATED against the current,
-//           re-based origin with the same fixed-order fp32 arithmetic as the parity oracle.  This applies
-//           the reference's "advance the origin by 1e-4 and query again with back-face culling" rule
-//           exactly (entries that fell behind the advanced origin are dropped) and keeps
-//           the origin bit-identical to the one the reference loop would carry;
-//   refill: when a full buffer has been drained and the ray is still alive, the next pass starts from
-//           the current origin.  The ray stops on miss, max_depth, or (rf) beta <= t_cutoff.
+// Algorithm (one thread per ray, rays walked in 8x4 pixel tiles per warp, loops warp-uniform):
+//   The ray is cut into consecutive intervals [t_start, t_start + delta] (delta adapts per ray so that an
+//   interval holds about a dozen entries).  Per interval:
+//   phase 1 (collect)  stack traversal of the LBVH restricted to the interval; leaves are only APPENDED to a
+//                      per-thread candidate list in shared memory.  No test result feeds back into the walk, so
+//                      the 32 lanes of a warp stay in the node loop together (the per-lane k-buffer version
+//                      measured 7 active lanes of 32 here);
+//   phase 2 (test)     every candidate gets the ray/ellipsoid entry distance from the pre-transformed SoA
+//                      record (48 B); entries inside the interval stay in the list;
+//   phase 3 (drain)    entries are taken in increasing distance; each is RE-EVALUATED against the current,
+//                      re-based origin with the same fixed-order fp32 arithmetic as the parity oracle.  This
+//                      applies the reference's "advance the origin by 1e-4 and query again with back-face
+//                      culling" rule exactly (entries that fell behind the advanced origin are dropped, SURVEY
+//                      quirk Q1) and keeps the origin bit-identical to the one the reference loop carries.
+//   The ray stops on leaving the scene box (miss), max_depth, or (rf) beta <= t_cutoff.  If one interval holds
+//   more candidates than the list (pathological overlap) the interval is halved; below a minimum width the lane
+//   falls back to a plain closest-hit walk for that step.
 // The adjoint either replays recorded hit lists (no BVH access) or re-traces like the primal.
 #include "vp_internal.cuh"
 
@@ -22,10 +29,12 @@
 
 namespace {
 
-constexpr int KBUF = 16;       // k-buffer entries per ray
-constexpr int STACK_MAX = 96;  // LBVH depth bound: 63 Morton bits + index tie-break bits
+constexpr int CAND_CAP = 48;     // candidate / hit list entries per ray (shared memory: 8 B each)
+constexpr int TARGET_HITS = 12;  // the interval width adapts towards this many entries per interval
+constexpr int STACK_MAX = 96;    // LBVH depth bound: 63 Morton bits + index tie-break bits
 constexpr int TRACE_THREADS = 128;
 constexpr int NODE_SENTINEL = 0x7fffffff;
+constexpr size_t TRACE_SMEM = (size_t)CAND_CAP * TRACE_THREADS * 8;
 #define VP_INF __int_as_float(0x7f800000)
 
 struct Isect {
@@ -70,112 +79,187 @@ struct Counters {
     uint32_t hits, candidates, nodes, passes, overflow;
 };
 
-// sorted insertion into the register k-buffer (ascending t; ties keep the lower sorted position first)
-__device__ __forceinline__ void kbuf_insert(float (&bt)[KBUF], int (&bi)[KBUF], float t, int id)
+// Approximate entry distance from the pre-transformed record xf (rows of M = diag(1/(extent s)) R^T with the
+// centre in .w).  Only used to ORDER candidates and to bin them into intervals; validity is conservative
+// (slightly negative discriminants pass) because the drain phase repeats the test exactly.
+__device__ __forceinline__ bool fast_isect(const DevScene &S, int pos, float3 o, float3 d, float &tn)
 {
-#pragma unroll
-    for (int i = 0; i < KBUF; ++i) {
-        bool sw = (t < bt[i]) || (t == bt[i] && id < bi[i]);
-        float tt = sw ? bt[i] : t;
-        int ti = sw ? bi[i] : id;
-        bt[i] = sw ? t : bt[i];
-        bi[i] = sw ? id : bi[i];
-        t = tt;
-        id = ti;
-    }
+    const float4 *x = S.xf + 3ll * pos;
+    float4 r0 = __ldg(x), r1 = __ldg(x + 1), r2 = __ldg(x + 2);
+    float3 v = make_float3(o.x - r0.w, o.y - r1.w, o.z - r2.w);
+    float3 oo = make_float3(r0.x * v.x + r0.y * v.y + r0.z * v.z, r1.x * v.x + r1.y * v.y + r1.z * v.z,
+                            r2.x * v.x + r2.y * v.y + r2.z * v.z);
+    float3 dd = make_float3(r0.x * d.x + r0.y * d.y + r0.z * d.z, r1.x * d.x + r1.y * d.y + r1.z * d.z,
+                            r2.x * d.x + r2.y * d.y + r2.z * d.z);
+    float a = dd.x * dd.x + dd.y * dd.y + dd.z * dd.z;
+    float b = -(oo.x * dd.x + oo.y * dd.y + oo.z * dd.z);
+    float c = oo.x * oo.x + oo.y * oo.y + oo.z * oo.z - 1.f;
+    float ba = __fdividef(b, a);
+    float lx = fmaf(ba, dd.x, oo.x), ly = fmaf(ba, dd.y, oo.y), lz = fmaf(ba, dd.z, oo.z);
+    float discr = 1.f - (lx * lx + ly * ly + lz * lz);
+    if (!(discr >= -2e-4f) || !(a > 0.f)) return false;
+    float sq = sqrtf(a * fmaxf(discr, 0.f));
+    float q = b + copysignf(sq, b);
+    float x0 = __fdividef(c, q), x1 = __fdividef(q, a);
+    tn = fminf(x0, x1);
+    return tn == tn;
 }
 
-__device__ __forceinline__ void leaf_test(const DevScene &S, int pos, float3 o, float3 d, float (&bt)[KBUF],
-                                          int (&bi)[KBUF], Counters &cn)
-{
-    float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
-    Mat3 R = vp_quat_to_matrix_rn(g2);
-    Isect is = exact_isect(o, d, g0, g1, R, S.extent);
-    cn.candidates++;
-    // front face in front of the origin; back faces are culled (RayFlags.BackfaceCulling, rf:127)
-    if (is.valid && is.tn > 0.f && (is.tn < bt[KBUF - 1] || (is.tn == bt[KBUF - 1] && pos < bi[KBUF - 1])))
-        kbuf_insert(bt, bi, is.tn, pos);
-}
-
-__device__ __forceinline__ bool slab(float3 lo, float3 hi, float3 o, float3 inv, float tlim, float &t0)
+// ray / box slab test against the interval [t_lo, t_hi]
+__device__ __forceinline__ bool slab(float3 lo, float3 hi, float3 o, float3 inv, float t_lo, float t_hi)
 {
     float ax = (lo.x - o.x) * inv.x, bx = (hi.x - o.x) * inv.x;
     float ay = (lo.y - o.y) * inv.y, by = (hi.y - o.y) * inv.y;
     float az = (lo.z - o.z) * inv.z, bz = (hi.z - o.z) * inv.z;
-    t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
-    float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tlim));
+    float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t_lo));
+    float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t_hi));
     // boxes are padded at build time; widen the exit by a few ulp for the reciprocal's rounding
-    return t0 <= t1 * 1.0000005f;
+    return t0 <= t1 * 1.0000005f + 1e-30f;
 }
 
-// One k-buffer pass: the K closest front-face entries seen from origin o.
-//
-// WARP-CONVERGENT: all 32 lanes of the warp call this together (lanes without work pass active = false).
-// The walk alternates two phases so that the expensive leaf work is executed by many lanes at once instead
-// of by the one or two lanes that happen to sit on a leaf (measured: 2.1 active lanes per k-buffer insert
-// in the naive per-lane loop):
-//   phase 1  every lane descends through internal nodes until it holds a leaf (or has finished);
-//   phase 2  the lanes holding a leaf run the exact ray/ellipsoid test + k-buffer insert together.
-__device__ __forceinline__ void fill_pass(const DevScene &S, float3 o, float3 d, bool active, float (&bt)[KBUF],
-                                          int (&bi)[KBUF], Counters &cn)
+// Walks one ray front to back and calls on_hit(pos, g0, g1, g2, R, isect) for every accepted entry, in the
+// reference's order.  on_hit evaluates the primitive, advances the origin `o` (captured by the caller) and
+// returns false to terminate the ray.  WARP-CONVERGENT: all 32 lanes call it (lanes without a ray pass
+// alive = false).  s_id / s_t are this thread's columns of the shared candidate list (stride TRACE_THREADS).
+template <class OnHit>
+__device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_t, const float3 &o, const float3 o0,
+                                         const float3 d, const float maxt, bool alive, bool &missed, Counters &cn,
+                                         OnHit &&on_hit)
 {
-#pragma unroll
-    for (int i = 0; i < KBUF; ++i) { bt[i] = VP_INF; bi[i] = -1; }
-    if (active) cn.passes++;
-    if (S.n <= 0) return;
-    if (S.root < 0) {
-        if (active) leaf_test(S, ~S.root, o, d, bt, bi, cn);
-        return;
-    }
+    missed = false;
+    if (S.n <= 0) { missed = alive; return; }
     float3 inv;
     inv.x = 1.f / (fabsf(d.x) > 1e-30f ? d.x : copysignf(1e-30f, d.x));
     inv.y = 1.f / (fabsf(d.y) > 1e-30f ? d.y : copysignf(1e-30f, d.y));
     inv.z = 1.f / (fabsf(d.z) > 1e-30f ? d.z : copysignf(1e-30f, d.z));
-    int stack_n[STACK_MAX];
-    float stack_t[STACK_MAX];
-    int sp = 0;
-    int node = active ? S.root : NODE_SENTINEL;
-    while (true) {
-        // ---- phase 1: internal nodes ----
-        while ((unsigned)node < (unsigned)NODE_SENTINEL) {
+    // all interval distances are measured from the ORIGINAL origin o0; `o` is the re-based origin
+    float t_start = 0.f, t_stop = VP_INF;
+    const float delta0 = __ldg(S.info + 6);
+    if (S.root >= 0) {
+        const float3 lo = make_float3(__ldg(S.info), __ldg(S.info + 1), __ldg(S.info + 2));
+        const float3 hi = make_float3(__ldg(S.info + 3), __ldg(S.info + 4), __ldg(S.info + 5));
+        float ax = (lo.x - o0.x) * inv.x, bx = (hi.x - o0.x) * inv.x;
+        float ay = (lo.y - o0.y) * inv.y, by = (hi.y - o0.y) * inv.y;
+        float az = (lo.z - o0.z) * inv.z, bz = (hi.z - o0.z) * inv.z;
+        t_start = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+        t_stop = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.000001f;
+        if (alive && !(t_start <= t_stop)) { missed = true; alive = false; }
+        t_start = fmaxf(t_start * 0.999999f - 1e-6f, 0.f);
+    }
+    float delta = delta0;
+    const float delta_min = delta0 * (1.f / 4096.f);
+    bool closest_mode = false, strict_lo = false;
+    int closest_left = 0;
+    int stack[STACK_MAX];
+    while (__any_sync(0xffffffffu, alive)) {
+        const float t_lo = strict_lo ? t_start : t_start - (1e-4f + 1e-5f * t_start);
+        float t_end = (S.root >= 0 && !closest_mode) ? t_start + delta : VP_INF;
+        int n_c = 0;
+        bool overflow = false;
+        float best_t = VP_INF;
+        int best_pos = -1;
+        if (alive) cn.passes++;
+        // ---- phase 1: collect the leaves whose boxes meet [t_lo, t_end] ----
+        int node = alive ? S.root : NODE_SENTINEL;
+        int sp = 0;
+        while (node != NODE_SENTINEL) {
+            if (node < 0) {
+                const int pos = ~node;
+                if (closest_mode) {
+                    float tn;
+                    cn.candidates++;
+                    if (fast_isect(S, pos, o0, d, tn) && tn > t_lo && tn < best_t) {
+                        best_t = tn;
+                        best_pos = pos;
+                        t_end = tn;  // nothing beyond the closest entry is needed
+                    }
+                } else if (n_c < CAND_CAP) {
+                    s_id[n_c * TRACE_THREADS] = pos;
+                    ++n_c;
+                } else {
+                    overflow = true;
+                    sp = 0;
+                }
+                node = sp > 0 ? stack[--sp] : NODE_SENTINEL;
+                continue;
+            }
             const float4 *nd = S.nodes + 4ll * node;
             float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
             cn.nodes++;
-            float tlim = bt[KBUF - 1];
-            float tl, tr;
-            bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), o, inv, tlim, tl);
-            bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), o, inv, tlim, tr);
+            bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), o0, inv, t_lo, t_end);
+            bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), o0, inv, t_lo, t_end);
             int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
             if (hl && hr) {
-                bool lfirst = tl <= tr;
-                int far_n = lfirst ? right : left;
-                float far_t = lfirst ? tr : tl;
-                node = lfirst ? left : right;
-                if (sp < STACK_MAX) { stack_n[sp] = far_n; stack_t[sp] = far_t; ++sp; }
+                node = left;
+                if (sp < STACK_MAX) stack[sp++] = right;
                 else cn.overflow++;
             } else if (hl) {
                 node = left;
             } else if (hr) {
                 node = right;
             } else {
-                node = NODE_SENTINEL;
-                while (sp > 0) {
-                    --sp;
-                    if (stack_t[sp] <= bt[KBUF - 1]) { node = stack_n[sp]; break; }
-                }
-            }
-        }
-        if (!__any_sync(0xffffffffu, node != NODE_SENTINEL)) break;
-        // ---- phase 2: leaves ----
-        if (node != NODE_SENTINEL) {
-            leaf_test(S, ~node, o, d, bt, bi, cn);
-            node = NODE_SENTINEL;
-            while (sp > 0) {
-                --sp;
-                if (stack_t[sp] <= bt[KBUF - 1]) { node = stack_n[sp]; break; }
+                node = sp > 0 ? stack[--sp] : NODE_SENTINEL;
             }
         }
         __syncwarp();
+        // ---- phase 2: entry distances; keep the entries inside the interval ----
+        int n_h = 0;
+        if (closest_mode) {
+            if (best_pos >= 0) { s_id[0] = best_pos; s_t[0] = best_t; n_h = 1; }
+        } else if (!overflow) {
+            for (int k = 0; k < n_c; ++k) {
+                const int pos = s_id[k * TRACE_THREADS];
+                float tn;
+                bool ok;
+                if (S.root >= 0) ok = fast_isect(S, pos, o0, d, tn);
+                else { ok = true; tn = 1.f; }
+                if (ok && tn > t_lo && tn <= t_end) {
+                    s_id[n_h * TRACE_THREADS] = pos;
+                    s_t[n_h * TRACE_THREADS] = tn;
+                    ++n_h;
+                }
+            }
+            cn.candidates += n_c;
+        }
+        __syncwarp();
+        // ---- phase 3: drain in increasing distance ----
+        const int n_found = n_h;
+        for (int taken = 0; alive && taken < n_found; ++taken) {
+            float bt = VP_INF;
+            int bk = 0;
+            for (int k = 0; k < n_found; ++k) {
+                float tk = s_t[k * TRACE_THREADS];
+                if (tk < bt) { bt = tk; bk = k; }
+            }
+            const int pos = s_id[bk * TRACE_THREADS];
+            s_t[bk * TRACE_THREADS] = VP_INF;
+            float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
+            Mat3 Rm = vp_quat_to_matrix_rn(g2);
+            Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
+            if (!is.valid || !(is.tn > 0.f)) continue;      // entry fell behind the advanced origin (Q1)
+            if (!(is.tn <= maxt)) { missed = true; alive = false; break; }
+            if (!on_hit(pos, g0, g1, g2, Rm, is)) { alive = false; break; }
+        }
+        // ---- next interval ----
+        if (alive) {
+            if (S.root < 0) { missed = true; alive = false; }
+            else if (overflow) {
+                delta *= 0.5f;
+                if (delta < delta_min) { closest_mode = true; closest_left = 8; }
+            } else if (closest_mode) {
+                if (best_pos < 0) { missed = true; alive = false; }   // nothing in front of t_start at all
+                else {
+                    t_start = best_t;      // strictly beyond the entry just handled
+                    strict_lo = true;
+                    if (--closest_left <= 0) { closest_mode = false; delta = delta_min * 8.f; }
+                }
+            } else {
+                strict_lo = false;
+                t_start = t_end;
+                delta *= (n_found == 0) ? 4.f : fminf(fmaxf((float)TARGET_HITS / (float)n_found, 0.5f), 2.f);
+            }
+            if (alive && t_start > t_stop) { missed = true; alive = false; }
+        }
     }
 }
 
@@ -378,6 +462,9 @@ struct TraceArgs {
 template <int INTEG, int KERNEL, int D>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_forward(DevScene S, vp_params P, TraceArgs A)
 {
+    extern __shared__ float4 smem_raw[];
+    int *s_id = reinterpret_cast<int *>(smem_raw) + threadIdx.x;
+    float *s_t = reinterpret_cast<float *>(smem_raw) + CAND_CAP * TRACE_THREADS + threadIdx.x;
     const int64_t t = (int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x;
     Counters cn = { 0, 0, 0, 0, 0 };
     const bool in_range = t < A.R;
@@ -389,61 +476,49 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_forward(DevScene S, vp_
         d = make_float3(A.d[3 * r], A.d[3 * r + 1], A.d[3 * r + 2]);
         if (A.maxt) maxt = A.maxt[r];
     }
+    const float3 o0 = o;
     float beta = 1.f, L[3] = { 0.f, 0.f, 0.f };
     uint32_t depth = 0;
-    bool missed = false, alive = in_range;
-    float bt[KBUF];
-    int bi[KBUF];
-    // the loop is warp-uniform: finished lanes keep voting so that fill_pass stays convergent
-    while (__any_sync(0xffffffffu, alive)) {
-        fill_pass(S, o, d, alive, bt, bi, cn);
-        const bool full = bt[KBUF - 1] < VP_INF;
-        constexpr int NY = (D >= 0) ? (D + 1) * (D + 1) : 1;
-        float Y[NY];
-        if constexpr (INTEG == VP_INTEGRATOR_RF && D >= 0) sh_basis<(D >= 0 ? D : 0)>(d, Y);
-#pragma unroll 1
-        while (alive && bt[0] < VP_INF) {
-            const int pos = bi[0];
+    bool missed = false;
+    constexpr int NY = (D >= 0) ? (D + 1) * (D + 1) : 1;
+    float Y[NY];
+    if constexpr (INTEG == VP_INTEGRATOR_RF && D >= 0) sh_basis<(D >= 0 ? D : 0)>(d, Y);
+    else Y[0] = 0.f;
+
+    walk_ray(S, s_id, s_t, o, o0, d, maxt, in_range, missed, cn,
+             [&](int pos, float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is) -> bool {
+        float T;
+        if constexpr (INTEG == VP_INTEGRATOR_RF) {
+            RfEval e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
+            T = e.T;
+            float raw[3] = { 0.f, 0.f, 0.f };
+            if constexpr (D >= 0) sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw);
+            const float omt = 1.f - T;
 #pragma unroll
-            for (int i = 0; i < KBUF - 1; ++i) { bt[i] = bt[i + 1]; bi[i] = bi[i + 1]; }
-            bt[KBUF - 1] = VP_INF;
-            float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
-            Mat3 Rm = vp_quat_to_matrix_rn(g2);
-            Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
-            if (!is.valid || !(is.tn > 0.f)) continue;      // entry fell behind the advanced origin (Q1)
-            if (!(is.tn <= maxt)) { missed = true; alive = false; break; }
-            float T;
-            if constexpr (INTEG == VP_INTEGRATOR_RF) {
-                RfEval e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
-                T = e.T;
-                float raw[3] = { 0.f, 0.f, 0.f };
-                if constexpr (D >= 0) sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw);
-                const float omt = 1.f - T;
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    float col = (D >= 0) ? fmaxf(raw[ch], 0.f) : 0.f;
-                    float le = beta * omt * col;           // rf:140
-                    if (!isfinite(le)) le = 0.f;            // rf:141
-                    L[ch] += le;                            // rf:145
-                }
-            } else {
-                float rho = (KERNEL == VP_KERNEL_GAUSSIAN) ? gauss_density_integral(g1, is)
-                                                           : epan_density_integral(o, d, g0, g1, Rm, is);
-                T = expf(-rho * g0.w);                      // tomo:44
+            for (int ch = 0; ch < 3; ++ch) {
+                float col = (D >= 0) ? fmaxf(raw[ch], 0.f) : 0.f;
+                float le = beta * omt * col;           // rf:140
+                if (!isfinite(le)) le = 0.f;            // rf:141
+                L[ch] += le;                            // rf:145
             }
-            beta *= T;                                      // rf:146 / tomo:85
-            if (A.ids && depth < (uint32_t)A.cap) A.ids[r * A.rs + depth * A.hs] = __float_as_int(g1.w);
-            // ray.o = si.p + ray.d * 1e-4                     rf:149 / tomo:114
-            o.x = fmaf(d.x, P.eps_advance, fmaf(d.x, is.tn, o.x));
-            o.y = fmaf(d.y, P.eps_advance, fmaf(d.y, is.tn, o.y));
-            o.z = fmaf(d.z, P.eps_advance, fmaf(d.z, is.tn, o.z));
-            depth += 1;
-            cn.hits++;
-            if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) { alive = false; break; }  // rf:173-174
-            if (!(depth < P.max_depth)) { alive = false; break; }                             // rf:186
+        } else {
+            float rho = (KERNEL == VP_KERNEL_GAUSSIAN) ? gauss_density_integral(g1, is)
+                                                       : epan_density_integral(o, d, g0, g1, Rm, is);
+            T = expf(-rho * g0.w);                      // tomo:44
         }
-        if (alive && !full) { missed = true; alive = false; }
-    }
+        beta *= T;                                      // rf:146 / tomo:85
+        if (A.ids && depth < (uint32_t)A.cap) A.ids[r * A.rs + depth * A.hs] = __float_as_int(g1.w);
+        // ray.o = si.p + ray.d * 1e-4                     rf:149 / tomo:114
+        o.x = fmaf(d.x, P.eps_advance, fmaf(d.x, is.tn, o.x));
+        o.y = fmaf(d.y, P.eps_advance, fmaf(d.y, is.tn, o.y));
+        o.z = fmaf(d.z, P.eps_advance, fmaf(d.z, is.tn, o.z));
+        depth += 1;
+        cn.hits++;
+        if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) return false;  // rf:173-174
+        if (!(depth < P.max_depth)) return false;                             // rf:186
+        return true;
+    });
+
     if (in_range) {
         if (INTEG == VP_INTEGRATOR_TOMO && missed && !(depth == 0 && P.hide_emitters)) {
 #pragma unroll
@@ -647,13 +722,16 @@ __device__ __forceinline__ float tomo_adjoint_hit(const DevScene &S, const Trace
 template <int INTEG, int KERNEL, int D, bool REPLAY>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_adjoint(DevScene S, vp_params P, TraceArgs A)
 {
+    extern __shared__ float4 smem_raw[];
+    int *s_id = reinterpret_cast<int *>(smem_raw) + threadIdx.x;
+    float *s_t = reinterpret_cast<float *>(smem_raw) + CAND_CAP * TRACE_THREADS + threadIdx.x;
     const int64_t t = (int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x;
     Counters cn = { 0, 0, 0, 0, 0 };
     const bool in_range = t < A.R;
     const int64_t r = in_range ? ray_index(t, P.image_width, P.image_height) : 0;
     float g[3] = { 0.f, 0.f, 0.f };
     if (in_range) { g[0] = A.dL[3 * r]; g[1] = A.dL[3 * r + 1]; g[2] = A.dL[3 * r + 2]; }
-    bool alive = in_range && (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f);   // rf:111-112
+    const bool alive = in_range && (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f);   // rf:111-112
     float3 o = make_float3(0.f, 0.f, 0.f), d = make_float3(0.f, 0.f, 1.f);
     float maxt = FLT_MAX;
     float L[3] = { 0.f, 0.f, 0.f };
@@ -663,6 +741,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_adjoint(DevScene S, vp_
         if (A.maxt) maxt = A.maxt[r];
         L[0] = A.state_in[3 * r]; L[1] = A.state_in[3 * r + 1]; L[2] = A.state_in[3 * r + 2];
     }
+    const float3 o0 = o;
     float beta = 1.f;
     uint32_t depth = 0;
     constexpr int NY = (D >= 0) ? (D + 1) * (D + 1) : 1;
@@ -670,7 +749,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_adjoint(DevScene S, vp_
     if constexpr (INTEG == VP_INTEGRATOR_RF && D >= 0) sh_basis<(D >= 0 ? D : 0)>(d, Y);
     else Y[0] = 0.f;
 
-    auto interact = [&](int pos, float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is) {
+    auto interact = [&](int pos, float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is) -> bool {
         float T;
         if constexpr (INTEG == VP_INTEGRATOR_RF)
             T = rf_adjoint_hit<KERNEL, D>(S, A, pos, o, d, g0, g1, g2, Rm, is, beta, g, L, Y);
@@ -682,6 +761,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_adjoint(DevScene S, vp_
         o.z = fmaf(d.z, P.eps_advance, fmaf(d.z, is.tn, o.z));
         depth += 1;
         cn.hits++;
+        if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) return false;
+        if (!(depth < P.max_depth)) return false;
+        return true;
     };
 
     if constexpr (REPLAY) {
@@ -699,28 +781,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_adjoint(DevScene S, vp_
             }
         }
     } else {
-        float bt[KBUF];
-        int bi[KBUF];
-        while (__any_sync(0xffffffffu, alive)) {
-            fill_pass(S, o, d, alive, bt, bi, cn);
-            const bool full = bt[KBUF - 1] < VP_INF;
-#pragma unroll 1
-            while (alive && bt[0] < VP_INF) {
-                const int pos = bi[0];
-#pragma unroll
-                for (int i = 0; i < KBUF - 1; ++i) { bt[i] = bt[i + 1]; bi[i] = bi[i + 1]; }
-                bt[KBUF - 1] = VP_INF;
-                float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
-                Mat3 Rm = vp_quat_to_matrix_rn(g2);
-                Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
-                if (!is.valid || !(is.tn > 0.f)) continue;
-                if (!(is.tn <= maxt)) { alive = false; break; }
-                interact(pos, g0, g1, g2, Rm, is);
-                if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) { alive = false; break; }
-                if (!(depth < P.max_depth)) { alive = false; break; }
-            }
-            if (alive && !full) alive = false;
-        }
+        bool missed = false;
+        walk_ray(S, s_id, s_t, o, o0, d, maxt, alive, missed, cn, interact);
     }
     flush_counters(cn, A.stats);
 }
@@ -760,7 +822,7 @@ template <int INTEG, int KERNEL, int D>
 void launch_forward(const DevScene &S, const vp_params &P, const TraceArgs &A, cudaStream_t st)
 {
     int64_t blocks = (A.R + TRACE_THREADS - 1) / TRACE_THREADS;
-    k_trace_forward<INTEG, KERNEL, D><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
+    k_trace_forward<INTEG, KERNEL, D><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
 }
 
 template <int INTEG, int KERNEL, int D>
@@ -768,7 +830,7 @@ void launch_adjoint(const DevScene &S, const vp_params &P, const TraceArgs &A, c
 {
     int64_t blocks = (A.R + TRACE_THREADS - 1) / TRACE_THREADS;
     if (A.rec_ids) k_trace_adjoint<INTEG, KERNEL, D, true><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
-    else k_trace_adjoint<INTEG, KERNEL, D, false><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
+    else k_trace_adjoint<INTEG, KERNEL, D, false><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
 }
 
 template <bool FWD>
