@@ -148,3 +148,21 @@ def test_edge_cases_empty_single_and_missing_rays():
     assert res0.nhits.cpu().tolist() == [0, 0, 0] and float(res0.rgb.abs().max()) == 0.0
     r_empty = acc.trace_forward(p, torch.zeros((0, 3)), torch.zeros((0, 3)))
     assert r_empty.rgb.shape == (0, 3)
+
+
+def test_dense_overlap_falls_back_to_closest_hit_search():
+    """More candidates in one interval than the shared-memory list holds (48): 300 nested ellipsoids."""
+    rng = np.random.default_rng(3)
+    n = 300
+    cloud = synthetic.make_cloud(n, 0.05, seed=3, sh_degree=1)
+    cloud.data[:, 0:3] = rng.normal(0, 0.003, size=(n, 3))
+    cloud.data[:, 3:6] = (0.05 + 0.25 * rng.random((n, 1))) * (1 + 0.2 * rng.random((n, 3)))
+    cloud.opacities[:] = 0.02
+    o, d, mt = _rays(view=0, w=32, h=16)
+    p, op = make_params(0, 0, max_depth=-1)
+    acc = gpu_scene(cloud)
+    res = acc.trace_forward(p, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt), record_cap=320)
+    ref = oracle_scene(cloud).forward(op, o, d, mt, cap=320, fragility=True)
+    st = compare_forward(res, ref, 320, max_fragile_frac=0.02)
+    assert ref.nhits.max() > 100
+    print(st)
