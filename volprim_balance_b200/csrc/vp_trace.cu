@@ -160,45 +160,68 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
         int best_pos = -1;
         if (alive) cn.passes++;
         // ---- phase 1: collect the leaves whose boxes meet [t_lo, t_end] ----
-        int node = alive ? S.root : NODE_SENTINEL;
+        // The loop body is branch-free per lane (predicated appends / push / pop): lanes differ only in their
+        // trip count.  Leaves are appended from their parent and never become the current node.
+        int node = (alive && !closest_mode && S.root >= 0) ? S.root : NODE_SENTINEL;
         int sp = 0;
+        if (alive && S.root < 0) { s_id[0] = ~S.root; n_c = 1; }       // single-primitive scene
         while (node != NODE_SENTINEL) {
-            if (node < 0) {
-                const int pos = ~node;
-                if (closest_mode) {
-                    float tn;
-                    cn.candidates++;
-                    if (fast_isect(S, pos, o0, d, tn) && tn > t_lo && tn < best_t) {
-                        best_t = tn;
-                        best_pos = pos;
-                        t_end = tn;  // nothing beyond the closest entry is needed
-                    }
-                } else if (n_c < CAND_CAP) {
-                    s_id[n_c * TRACE_THREADS] = pos;
-                    ++n_c;
-                } else {
-                    overflow = true;
-                    sp = 0;
-                }
-                node = sp > 0 ? stack[--sp] : NODE_SENTINEL;
-                continue;
-            }
             const float4 *nd = S.nodes + 4ll * node;
             float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+            const int top = stack[sp > 0 ? sp - 1 : 0];                   // speculative: used only on a pop
             cn.nodes++;
-            bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), o0, inv, t_lo, t_end);
-            bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), o0, inv, t_lo, t_end);
-            int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
-            if (hl && hr) {
-                node = left;
+            const bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), o0, inv, t_lo, t_end);
+            const bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), o0, inv, t_lo, t_end);
+            const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
+            if (hl && left < 0) {
+                if (n_c < CAND_CAP) s_id[n_c * TRACE_THREADS] = ~left;
+                ++n_c;
+            }
+            if (hr && right < 0) {
+                if (n_c < CAND_CAP) s_id[n_c * TRACE_THREADS] = ~right;
+                ++n_c;
+            }
+            const bool vl = hl && left >= 0, vr = hr && right >= 0;
+            if (vl && vr) {
                 if (sp < STACK_MAX) stack[sp++] = right;
                 else cn.overflow++;
-            } else if (hl) {
                 node = left;
-            } else if (hr) {
-                node = right;
             } else {
-                node = sp > 0 ? stack[--sp] : NODE_SENTINEL;
+                const bool pop = !vl && !vr;
+                node = vl ? left : (vr ? right : (sp > 0 ? top : NODE_SENTINEL));
+                sp -= (pop && sp > 0) ? 1 : 0;
+            }
+            if (n_c > CAND_CAP) node = NODE_SENTINEL;                     // list overflow: abandon the interval
+        }
+        if (n_c > CAND_CAP) { overflow = true; n_c = 0; }
+        // closest-hit walk (fallback for lanes whose interval cannot be listed; rare)
+        if (__any_sync(0xffffffffu, alive && closest_mode)) {
+            int cnode = (alive && closest_mode) ? S.root : NODE_SENTINEL;
+            sp = 0;
+            while (cnode != NODE_SENTINEL) {
+                if (cnode < 0) {
+                    float tn;
+                    cn.candidates++;
+                    if (fast_isect(S, ~cnode, o0, d, tn) && tn > t_lo && tn < best_t) {
+                        best_t = tn;
+                        best_pos = ~cnode;
+                        t_end = tn;  // nothing beyond the closest entry is needed
+                    }
+                    cnode = sp > 0 ? stack[--sp] : NODE_SENTINEL;
+                    continue;
+                }
+                const float4 *nd = S.nodes + 4ll * cnode;
+                float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+                cn.nodes++;
+                const bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), o0, inv, t_lo, t_end);
+                const bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), o0, inv, t_lo, t_end);
+                const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
+                if (hl && hr) {
+                    cnode = left;
+                    if (sp < STACK_MAX) stack[sp++] = right;
+                } else if (hl) cnode = left;
+                else if (hr) cnode = right;
+                else cnode = sp > 0 ? stack[--sp] : NODE_SENTINEL;
             }
         }
         __syncwarp();
