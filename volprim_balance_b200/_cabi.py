@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libvolprim_cuda.so")
+LIB_PATH = os.environ.get("VOLPRIM_CUDA_LIB", os.path.join(_PKG, "libvolprim_cuda.so"))  # override: kernel tuning experiments
 
 VP_OK = 0
 INTEGRATOR_RF, INTEGRATOR_TOMO = 0, 1

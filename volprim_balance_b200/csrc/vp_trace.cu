@@ -29,8 +29,14 @@
 
 namespace {
 
-constexpr int CAND_CAP = 48;     // candidate / hit list entries per ray (shared memory: 8 B each)
-constexpr int TARGET_HITS = 12;  // the interval width adapts towards this many entries per interval
+#ifndef VP_CAND_CAP
+#define VP_CAND_CAP 48
+#endif
+#ifndef VP_MIN_BLOCKS
+#define VP_MIN_BLOCKS 4
+#endif
+constexpr int CAND_CAP = VP_CAND_CAP;     // candidate / hit list entries per ray (shared memory: 8 B each)
+constexpr int TARGET_HITS = CAND_CAP / 4;  // the interval width adapts towards this many entries per interval
 constexpr int STACK_MAX = 96;    // LBVH depth bound: 63 Morton bits + index tie-break bits
 constexpr int TRACE_THREADS = 128;
 constexpr int NODE_SENTINEL = 0x7fffffff;
@@ -483,7 +489,7 @@ struct TraceArgs {
 
 // ---- forward ----------------------------------------------------------------------------------
 template <int INTEG, int KERNEL, int D>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_forward(DevScene S, vp_params P, TraceArgs A)
+__global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(DevScene S, vp_params P, TraceArgs A)
 {
     extern __shared__ float4 smem_raw[];
     int *s_id = reinterpret_cast<int *>(smem_raw) + threadIdx.x;
@@ -743,7 +749,7 @@ __device__ __forceinline__ float tomo_adjoint_hit(const DevScene &S, const Trace
 }
 
 template <int INTEG, int KERNEL, int D, bool REPLAY>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_adjoint(DevScene S, vp_params P, TraceArgs A)
+__global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_adjoint(DevScene S, vp_params P, TraceArgs A)
 {
     extern __shared__ float4 smem_raw[];
     int *s_id = reinterpret_cast<int *>(smem_raw) + threadIdx.x;
