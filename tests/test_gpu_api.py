@@ -1,0 +1,168 @@
+"""GPU: the public host API (load_dict / render / autograd adjoint) and full-size, size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import volprim_balance_b200 as vp
+from oracle import oracle as O
+from volprim_balance_b200 import synthetic
+from tests.parity_utils import RGB_ATOL, RGB_RTOL, compare_forward, gpu_scene, grad_close, make_params, oracle_scene
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _sensor_dict(cam, rfilter="box"):
+    return {"type": "perspective", "fov": cam.fov_x_deg, "fov_axis": "x", "to_world": vp.Transform4f(cam.to_world),
+            "near_clip": cam.near_clip, "far_clip": cam.far_clip,
+            "film": {"type": "hdrfilm", "width": cam.width, "height": cam.height, "rfilter": {"type": rfilter}}}
+
+
+def test_raygen_matches_perspective_sensor_restatement():
+    cam = synthetic.ring_camera(3, 8, 72, 40)
+    acc = gpu_scene(synthetic.make_cloud(4, 0.1, seed=0))
+    s = vp.PerspectiveSensor(_sensor_dict(cam))
+    o, d, mt = acc.raygen_perspective(s.vp_camera(), 1, None)
+    ro, rd, rmt = synthetic.camera_rays(cam)
+    np.testing.assert_allclose(o.cpu().numpy(), ro, atol=2e-6)
+    np.testing.assert_allclose(d.cpu().numpy(), rd, atol=2e-6)
+    np.testing.assert_allclose(mt.cpu().numpy(), rmt, rtol=1e-5)
+    jit = torch.rand(72 * 40 * 2, 2)
+    o2, d2, _ = acc.raygen_perspective(s.vp_camera(), 2, jit)
+    px = (np.repeat(np.arange(72 * 40), 2) % 72 + jit[:, 0].numpy()) / 72
+    py = (np.repeat(np.arange(72 * 40), 2) // 72 + jit[:, 1].numpy()) / 40
+    ro2, rd2, _ = synthetic.rays_from_samples(cam, px, py)
+    np.testing.assert_allclose(d2.cpu().numpy(), rd2, atol=2e-6)
+
+
+def test_cfg1_smoke_ply_tomography_256x256_16spp():
+    """BASELINE configs[0]: volprim_tomography on resources/smoke.ply, 256x256, 16 spp (4x4 stratified offsets)."""
+    scene = vp.load_dict({"type": "scene", "integrator": {"type": "volprim_tomography", "max_depth": -1},
+                          "primitives": {"type": "ellipsoidsmesh", "filename": os.path.join(GOLD, "smoke.ply"), "extent": 3.0},
+                          "environment": {"type": "constant"}})
+    shape = scene.ellipsoids()
+    assert shape.count == 835
+    cam = synthetic.Camera(synthetic.look_at([0, 0, 4], [0, 0, 0], [0, 1, 0]), 40.0, 256, 256)
+    offs = [((i + 0.5) / 4, (j + 0.5) / 4) for j in range(4) for i in range(4)]
+    o, d, mt = synthetic.camera_rays(cam, offs)
+    ray = vp.Ray3f(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(mt).cuda())
+    scene.integrator.record_cap = 256
+    L, valid, aovs, state = scene.integrator.sample(vp.ADMode.Primal, scene, None, ray, record=True)
+    res = scene.integrator.last
+    data = shape.data.cpu().numpy().reshape(-1, 10)
+    sig = shape.attributes["sigma_t"].cpu().numpy()
+    ref = O.Scene(data, sig, None, 3.0).forward(O.Params(integrator=O.TOMO, max_depth=-1), o, d, mt, cap=256, fragility=True)
+    st = compare_forward(res, ref, 256)
+    assert st["rays"] == 256 * 256 * 16 and ref.nhits.max() > 20
+    img = L.reshape(256, 256, 16, 3).mean(2)
+    assert 0.0 < float(img.min()) and float(img.max()) <= 1.0 + 1e-6
+    print(st)
+
+
+def test_render_autograd_matches_oracle_adjoint_reference_exact_and_corrected():
+    n = 3000
+    cloud = synthetic.make_cloud(n, synthetic.sigma0_for_hits(n, 25), seed=21, sh_degree=2)
+    cam = synthetic.ring_camera(5, 8, 48, 32)
+    scene = vp.load_dict({"type": "scene", "integrator": {"type": "volprim_rf", "max_depth": 64, "rr_depth": 64},
+                          "primitives": {"type": "ellipsoidsmesh", "centers": cloud.data[:, :3], "scales": cloud.data[:, 3:6],
+                                         "quaternions": cloud.data[:, 6:], "opacities": cloud.opacities[:, None],
+                                         "sh_coeffs": cloud.sh_coeffs, "extent": 3.0},
+                          "cam": _sensor_dict(cam)})
+    params = vp.traverse(scene)
+    keys = ["primitives.data", "primitives.opacities", "primitives.sh_coeffs"]
+    o, d, mt = synthetic.camera_rays(cam)
+    osc = oracle_scene(cloud)
+    w = torch.from_numpy(np.random.default_rng(2).normal(size=(32, 48, 3)).astype(np.float32)).cuda()
+    for mode in ("reference_exact", "corrected"):
+        for k in keys:
+            params[k].requires_grad_(True)
+            params[k].grad = None
+        img = vp.render(scene, params, sensor=0, spp=1, jitter=False, adjoint_mode=mode)
+        (img * w).sum().backward()
+        op = O.Params(integrator=O.RF, kernel=O.GAUSS, max_depth=64, srgb_primitives=(mode == "reference_exact"))
+        ref = osc.forward(op, o, d, mt, cap=64, fragility=True)
+        dL = w.reshape(-1, 3).cpu().numpy()
+        if mode == "reference_exact":   # state_in = linear output, delta-L applied in sRGB space (quirk Q3)
+            np.testing.assert_allclose(img.detach().reshape(-1, 3).cpu().numpy(), ref.rgb, atol=2e-4, rtol=2e-3)
+            rd, ra, rs = osc.adjoint(op, o, d, dL, ref.rgb, mt)
+        else:                           # true gradient: chain through srgb_to_linear, state_in in sRGB space
+            deriv = O.srgb_to_linear_deriv(ref.rgb)
+            rd, ra, rs = osc.adjoint(op, o, d, dL * deriv, ref.rgb, mt)
+        grad_close(params[keys[0]].grad.cpu().numpy(), rd, rtol=5e-3, what=f"{mode} d data")
+        grad_close(params[keys[1]].grad.cpu().numpy(), ra, rtol=5e-3, what=f"{mode} d opacities")
+        grad_close(params[keys[2]].grad.cpu().numpy(), rs, rtol=5e-3, what=f"{mode} d sh")
+
+
+def test_params_update_rebuild_and_refit_agree():
+    n = 20000
+    cloud = synthetic.make_cloud(n, synthetic.sigma0_for_hits(n, 30), seed=8)
+    o, d, mt = synthetic.camera_rays(synthetic.ring_camera(0, 8, 64, 32))
+    p, _ = make_params(0, 0, 64)
+    acc = gpu_scene(cloud)
+    moved = cloud.data.copy()
+    moved[:, :3] += np.random.default_rng(0).normal(0, 2e-3, (n, 3)).astype(np.float32)
+    to, td, tm = torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt)
+    acc.set_primitives(torch.from_numpy(moved), torch.from_numpy(cloud.opacities), torch.from_numpy(cloud.sh_coeffs), 3.0)
+    acc.refit()
+    a = acc.trace_forward(p, to, td, tm, record_cap=64)
+    acc.build()
+    b = acc.trace_forward(p, to, td, tm, record_cap=64)
+    assert torch.equal(a.hit_ids, b.hit_ids) and torch.equal(a.rgb, b.rgb)
+
+
+@pytest.fixture(scope="module")
+def cfg2():
+    n = 1_000_000
+    cloud = synthetic.make_cloud(n, synthetic.sigma0_for_hits(n, 60.0), seed=1)
+    cam = synthetic.ring_camera(0, 8, 1920, 1080)
+    o, d, mt = synthetic.camera_rays(cam)
+    return cloud, tuple(torch.from_numpy(x).cuda() for x in (o, d, mt)), (o, d, mt)
+
+
+def test_full_size_cfg2_properties(cfg2):
+    """1M primitives, 1920x1080: determinism, permutation invariance of the primitive order (different Morton
+    ties / BVH input order, same image and same hit lists after relabelling), max_depth prefix property, replayed
+    vs re-traced adjoint, and a 1/256 pixel subsample against the oracle."""
+    cloud, (o, d, mt), (on, dn, mtn) = cfg2
+    p, op = make_params(0, 0, 128, image=(1920, 1080))
+    acc = gpu_scene(cloud)
+    a = acc.trace_forward(p, o, d, mt, record_cap=128)
+    b = acc.trace_forward(p, o, d, mt, record_cap=128)
+    assert torch.equal(a.rgb, b.rgb) and torch.equal(a.hit_ids, b.hit_ids)            # bit-stable
+    st = acc.stats()
+    assert st["stack_overflows"] == 0 and 25 < st["hits"] / o.shape[0] < 40
+    # permutation of the primitive numbering
+    perm = np.random.default_rng(5).permutation(cloud.n)
+    acc2 = vp.accel.EllipsoidAccel()
+    acc2.set_primitives(torch.from_numpy(cloud.data[perm]), torch.from_numpy(cloud.opacities[perm]),
+                        torch.from_numpy(cloud.sh_coeffs[perm]), 3.0)
+    acc2.build()
+    c = acc2.trace_forward(p, o, d, mt, record_cap=128)
+    tperm = torch.from_numpy(perm).cuda()
+    relabelled = torch.where(c.hit_ids >= 0, tperm[c.hit_ids.clamp_min(0).long()].int(), c.hit_ids)
+    same = (relabelled == a.hit_ids).all(0)
+    assert float(same.float().mean()) > 0.9999                                        # exact-tie order may differ
+    assert torch.equal(c.rgb[same], a.rgb[same])
+    # max_depth prefix property
+    p8, _ = make_params(0, 0, 8, image=(1920, 1080))
+    e = acc.trace_forward(p8, o, d, mt, record_cap=8)
+    assert torch.equal(e.hit_ids, a.hit_ids[:8]) and torch.equal(e.nhits, a.nhits.clamp_max(8))
+    # replayed and re-traced adjoint see the same hit sequence
+    sub = slice(0, 1920 * 64)
+    dL = torch.randn(1920 * 64, 3, device="cuda")
+    pa, _ = make_params(0, 0, 128)
+    g1 = acc.trace_adjoint(pa, o[sub], d[sub], mt[sub], dL, a.rgb[sub], a.hit_ids[:, sub].contiguous(), a.nhits[sub])
+    g2 = acc.trace_adjoint(pa, o[sub], d[sub], mt[sub], dL, a.rgb[sub])
+    for x, y in zip(g1, g2):
+        grad_close(x.cpu().numpy(), y.cpu().numpy(), rtol=1e-3, what="replay vs retrace")
+    # oracle on every 16th pixel in x and y
+    sel = np.zeros((1080, 1920), bool)
+    sel[8::16, 8::16] = True
+    sel = sel.reshape(-1)
+    ref = oracle_scene(cloud).forward(op, on[sel], dn[sel], mtn[sel], cap=128, fragility=True)
+    tsel = torch.from_numpy(sel).cuda()
+    from volprim_balance_b200.accel import TraceResult
+    part = TraceResult(a.rgb[tsel], a.beta[tsel], a.nhits[tsel], a.hit_ids[:, tsel].contiguous())
+    print(compare_forward(part, ref, 128))
