@@ -152,7 +152,7 @@ def test_full_size_cfg2_properties(cfg2):
     # replayed and re-traced adjoint see the same hit sequence
     sub = slice(0, 1920 * 64)
     dL = torch.randn(1920 * 64, 3, device="cuda")
-    pa, _ = make_params(0, 0, 128)
+    pa, _ = make_params(0, 0, 128, image=(1920, 64))   # same (tile) walker as the recorded lists
     g1 = acc.trace_adjoint(pa, o[sub], d[sub], mt[sub], dL, a.rgb[sub], a.hit_ids[:, sub].contiguous(), a.nhits[sub])
     g2 = acc.trace_adjoint(pa, o[sub], d[sub], mt[sub], dL, a.rgb[sub])
     for x, y in zip(g1, g2):

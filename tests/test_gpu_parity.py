@@ -19,12 +19,14 @@ def _rays(view=0, w=64, h=48):
     return synthetic.camera_rays(cam)
 
 
+@pytest.mark.parametrize("tile", [False, True], ids=["per_ray", "tile"])
 @pytest.mark.parametrize("kernel", [0, 1])
 @pytest.mark.parametrize("deg", [0, 1, 2, 3])
-def test_rf_forward_matches_oracle(kernel, deg):
+def test_rf_forward_matches_oracle(kernel, deg, tile):
+    """tile=True: image-shaped launch -> warp-cooperative walker; False: explicit ray batch -> per-ray walker."""
     cloud = _cloud(deg=deg)
     o, d, mt = _rays()
-    p, op = make_params(0, kernel, max_depth=128)
+    p, op = make_params(0, kernel, max_depth=128, image=(64, 48) if tile else None)
     acc = gpu_scene(cloud)
     res = acc.trace_forward(p, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt), record_cap=128)
     ref = oracle_scene(cloud).forward(op, o, d, mt, cap=128, fragility=True)
@@ -33,13 +35,14 @@ def test_rf_forward_matches_oracle(kernel, deg):
     print(st, acc.stats())
 
 
+@pytest.mark.parametrize("tile", [False, True], ids=["per_ray", "tile"])
 @pytest.mark.parametrize("kernel", [0, 1])
-def test_tomography_forward_matches_oracle(kernel):
+def test_tomography_forward_matches_oracle(kernel, tile):
     cloud = _cloud(n=5000, crossings=20)
     cloud.extent = 3.0 if kernel == 0 else 1.0  # Epanechnikov integral is clamped to 0 at extent 3 (quirk Q4)
     sig = np.random.default_rng(5).uniform(0.0005, 0.02, cloud.n).astype(np.float32)
     o, d, mt = _rays(view=3)
-    p, op = make_params(1, kernel, max_depth=-1, env=(1.0, 0.5, 0.25))
+    p, op = make_params(1, kernel, max_depth=-1, env=(1.0, 0.5, 0.25), image=(64, 48) if tile else None)
     acc = gpu_scene(cloud, attr=sig, sh=False)
     res = acc.trace_forward(p, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt), record_cap=256)
     ref = oracle_scene(cloud, attr=sig, sh=False).forward(op, o, d, mt, cap=256, fragility=True)
@@ -48,11 +51,11 @@ def test_tomography_forward_matches_oracle(kernel):
     print(st)
 
 
-@pytest.mark.parametrize("kernel,replay", [(0, True), (0, False), (1, True)])
-def test_rf_adjoint_matches_oracle(kernel, replay):
+@pytest.mark.parametrize("kernel,replay,tile", [(0, True, False), (0, False, False), (1, True, True), (0, False, True)])
+def test_rf_adjoint_matches_oracle(kernel, replay, tile):
     cloud = _cloud(n=4000, crossings=30)
     o, d, mt = _rays(view=1, w=48, h=32)
-    p, op = make_params(0, kernel, max_depth=128)
+    p, op = make_params(0, kernel, max_depth=128, image=(48, 32) if tile else None)
     acc = gpu_scene(cloud)
     to, td, tm = torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt)
     fwd = acc.trace_forward(p, to, td, tm, record_cap=128)
@@ -159,10 +162,12 @@ def test_dense_overlap_falls_back_to_closest_hit_search():
     cloud.data[:, 3:6] = (0.05 + 0.25 * rng.random((n, 1))) * (1 + 0.2 * rng.random((n, 3)))
     cloud.opacities[:] = 0.02
     o, d, mt = _rays(view=0, w=32, h=16)
-    p, op = make_params(0, 0, max_depth=-1)
     acc = gpu_scene(cloud)
-    res = acc.trace_forward(p, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt), record_cap=320)
-    ref = oracle_scene(cloud).forward(op, o, d, mt, cap=320, fragility=True)
-    st = compare_forward(res, ref, 320, max_fragile_frac=0.02)
-    assert ref.nhits.max() > 100
-    print(st)
+    ref = None
+    for image in (None, (32, 16)):      # per-ray walker, and the tile walker handing over to it
+        p, op = make_params(0, 0, max_depth=-1, image=image)
+        res = acc.trace_forward(p, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt), record_cap=320)
+        ref = ref or oracle_scene(cloud).forward(op, o, d, mt, cap=320, fragility=True)
+        st = compare_forward(res, ref, 320, max_fragile_frac=0.02)
+        assert ref.nhits.max() > 100
+        print(st)

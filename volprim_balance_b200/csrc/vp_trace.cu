@@ -41,6 +41,11 @@ constexpr int STACK_MAX = 96;    // LBVH depth bound: 63 Morton bits + index tie
 constexpr int TRACE_THREADS = 128;
 constexpr int NODE_SENTINEL = 0x7fffffff;
 constexpr size_t TRACE_SMEM = (size_t)CAND_CAP * TRACE_THREADS * 8;
+// warp-cooperative (tile) walker: per-lane hit lists + per-warp node queue and tile candidate list
+constexpr int TILE_HIT_CAP = 32;
+constexpr int TILE_QCAP = 640;
+constexpr int TILE_CCAP = 384;
+constexpr size_t TILE_SMEM = (size_t)TILE_HIT_CAP * TRACE_THREADS * 8 + (size_t)(TRACE_THREADS / 32) * (TILE_QCAP + TILE_CCAP) * 4;
 #define VP_INF __int_as_float(0x7f800000)
 
 struct Isect {
@@ -112,15 +117,40 @@ __device__ __forceinline__ bool fast_isect(const DevScene &S, int pos, float3 o,
 }
 
 // ray / box slab test against the interval [t_lo, t_hi]
-__device__ __forceinline__ bool slab(float3 lo, float3 hi, float3 o, float3 inv, float t_lo, float t_hi)
+__device__ __forceinline__ bool slab(float3 lo, float3 hi, float3 oi, float3 inv, float t_lo, float t_hi)
 {
-    float ax = (lo.x - o.x) * inv.x, bx = (hi.x - o.x) * inv.x;
-    float ay = (lo.y - o.y) * inv.y, by = (hi.y - o.y) * inv.y;
-    float az = (lo.z - o.z) * inv.z, bz = (hi.z - o.z) * inv.z;
+    // oi = o * inv, so each plane distance is a single FMA
+    float ax = fmaf(lo.x, inv.x, -oi.x), bx = fmaf(hi.x, inv.x, -oi.x);
+    float ay = fmaf(lo.y, inv.y, -oi.y), by = fmaf(hi.y, inv.y, -oi.y);
+    float az = fmaf(lo.z, inv.z, -oi.z), bz = fmaf(hi.z, inv.z, -oi.z);
     float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t_lo));
     float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t_hi));
     // boxes are padded at build time; widen the exit by a few ulp for the reciprocal's rounding
-    return t0 <= t1 * 1.0000005f + 1e-30f;
+    return t0 <= t1 * 1.000001f + 1e-30f;
+}
+
+// phase 3 of both walkers: hand the listed entries to on_hit in increasing distance.  Each entry is RE-EVALUATED
+// against the current, re-based origin `o` with the oracle's fixed-order arithmetic (quirk Q1, see file header).
+template <int STRIDE, class OnHit>
+__device__ __forceinline__ void drain_list(const DevScene &S, const int *s_id, float *s_t, int n_found, const float3 &o,
+                                           const float3 d, float maxt, bool &alive, bool &missed, OnHit &&on_hit)
+{
+    for (int taken = 0; alive && taken < n_found; ++taken) {
+        float bt = VP_INF;
+        int bk = 0;
+        for (int k = 0; k < n_found; ++k) {
+            float tk = s_t[k * STRIDE];
+            if (tk < bt) { bt = tk; bk = k; }
+        }
+        const int pos = s_id[bk * STRIDE];
+        s_t[bk * STRIDE] = VP_INF;
+        float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
+        Mat3 Rm = vp_quat_to_matrix_rn(g2);
+        Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
+        if (!is.valid || !(is.tn > 0.f)) continue;      // entry fell behind the advanced origin (Q1)
+        if (!(is.tn <= maxt)) { missed = true; alive = false; break; }
+        if (!on_hit(pos, g0, g1, g2, Rm, is)) { alive = false; break; }
+    }
 }
 
 // Walks one ray front to back and calls on_hit(pos, g0, g1, g2, R, isect) for every accepted entry, in the
@@ -130,7 +160,7 @@ __device__ __forceinline__ bool slab(float3 lo, float3 hi, float3 o, float3 inv,
 template <class OnHit>
 __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_t, const float3 &o, const float3 o0,
                                          const float3 d, const float maxt, bool alive, bool &missed, Counters &cn,
-                                         OnHit &&on_hit)
+                                         OnHit &&on_hit, const float t_begin = 0.f)
 {
     missed = false;
     if (S.n <= 0) { missed = alive; return; }
@@ -138,6 +168,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
     inv.x = 1.f / (fabsf(d.x) > 1e-30f ? d.x : copysignf(1e-30f, d.x));
     inv.y = 1.f / (fabsf(d.y) > 1e-30f ? d.y : copysignf(1e-30f, d.y));
     inv.z = 1.f / (fabsf(d.z) > 1e-30f ? d.z : copysignf(1e-30f, d.z));
+    const float3 oi = make_float3(o0.x * inv.x, o0.y * inv.y, o0.z * inv.z);
     // all interval distances are measured from the ORIGINAL origin o0; `o` is the re-based origin
     float t_start = 0.f, t_stop = VP_INF;
     const float delta0 = __ldg(S.info + 6);
@@ -150,7 +181,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
         t_start = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
         t_stop = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.000001f;
         if (alive && !(t_start <= t_stop)) { missed = true; alive = false; }
-        t_start = fmaxf(t_start * 0.999999f - 1e-6f, 0.f);
+        t_start = fmaxf(fmaxf(t_start * 0.999999f - 1e-6f, 0.f), t_begin);
     }
     float delta = delta0;
     const float delta_min = delta0 * (1.f / 4096.f);
@@ -176,9 +207,13 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
             float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
             const int top = stack[sp > 0 ? sp - 1 : 0];                   // speculative: used only on a pop
             cn.nodes++;
-            const bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), o0, inv, t_lo, t_end);
-            const bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), o0, inv, t_lo, t_end);
+            const bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), oi, inv, t_lo, t_end);
+            const bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), oi, inv, t_lo, t_end);
             const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
+#ifdef VP_PREFETCH
+            if (left >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.nodes + 4ll * left));
+            if (right >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.nodes + 4ll * right));
+#endif
             if (hl && left < 0) {
                 if (n_c < CAND_CAP) s_id[n_c * TRACE_THREADS] = ~left;
                 ++n_c;
@@ -219,8 +254,8 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
                 const float4 *nd = S.nodes + 4ll * cnode;
                 float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
                 cn.nodes++;
-                const bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), o0, inv, t_lo, t_end);
-                const bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), o0, inv, t_lo, t_end);
+                const bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), oi, inv, t_lo, t_end);
+                const bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), oi, inv, t_lo, t_end);
                 const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
                 if (hl && hr) {
                     cnode = left;
@@ -253,22 +288,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
         __syncwarp();
         // ---- phase 3: drain in increasing distance ----
         const int n_found = n_h;
-        for (int taken = 0; alive && taken < n_found; ++taken) {
-            float bt = VP_INF;
-            int bk = 0;
-            for (int k = 0; k < n_found; ++k) {
-                float tk = s_t[k * TRACE_THREADS];
-                if (tk < bt) { bt = tk; bk = k; }
-            }
-            const int pos = s_id[bk * TRACE_THREADS];
-            s_t[bk * TRACE_THREADS] = VP_INF;
-            float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
-            Mat3 Rm = vp_quat_to_matrix_rn(g2);
-            Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
-            if (!is.valid || !(is.tn > 0.f)) continue;      // entry fell behind the advanced origin (Q1)
-            if (!(is.tn <= maxt)) { missed = true; alive = false; break; }
-            if (!on_hit(pos, g0, g1, g2, Rm, is)) { alive = false; break; }
-        }
+        drain_list<TRACE_THREADS>(S, s_id, s_t, n_found, o, d, maxt, alive, missed, on_hit);
         // ---- next interval ----
         if (alive) {
             if (S.root < 0) { missed = true; alive = false; }
@@ -289,6 +309,167 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
             }
             if (alive && t_start > t_stop) { missed = true; alive = false; }
         }
+    }
+}
+
+// Warp-cooperative walker for COHERENT rays (the 32 lanes of a warp are an 8x4 pixel tile).
+//
+// The per-ray walker spends three quarters of its time in ~600 DEPENDENT node visits per ray.  Here the warp walks
+// the tree ONCE per interval for the whole tile: the 32 ray segments of the interval are bounded by a capsule
+// (mean segment + largest deviation r), every step lets the 32 lanes test 32 DIFFERENT queued nodes against that
+// capsule (child boxes inflated by r), and ballots compact the surviving children into the shared queue / the
+// tile's candidate list.  Each lane then tests the tile's candidates against its own ray (warp-uniform, broadcast
+// loads) and drains its own hits exactly like the per-ray walker, so results are identical.
+// Interval bookkeeping is warp-uniform.  Pathological overlap (lists overflow below the minimum interval width)
+// hands the warp over to the per-ray walker.
+template <class OnHit>
+__device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const float3 &o, const float3 o0,
+                                          const float3 d, const float maxt, bool alive, bool &missed, Counters &cn,
+                                          OnHit &&on_hit)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // shared memory: [hit ids 32 x 128][hit t 32 x 128][per warp: node queue, tile candidates]; the per-ray
+    // fallback re-uses the same 48 KB as [ids 48 x 128][t 48 x 128]
+    int *s_id = smem + threadIdx.x;
+    float *s_t = reinterpret_cast<float *>(smem) + TILE_HIT_CAP * TRACE_THREADS + threadIdx.x;
+    int *w_queue = smem + 2 * TILE_HIT_CAP * TRACE_THREADS + (threadIdx.x >> 5) * (TILE_QCAP + TILE_CCAP);
+    int *w_cand = w_queue + TILE_QCAP;
+    int *fb_id = smem + threadIdx.x;
+    float *fb_t = reinterpret_cast<float *>(smem) + CAND_CAP * TRACE_THREADS + threadIdx.x;
+    static_assert(TILE_SMEM >= TRACE_SMEM, "the per-ray fallback lists must fit");
+    const unsigned lt = (1u << lane) - 1u;
+    missed = false;
+    if (S.n <= 0) { missed = alive; return; }
+    if (S.root < 0) {   // single primitive: nothing to share
+        walk_ray(S, fb_id, fb_t, o, o0, d, maxt, alive, missed, cn, on_hit);
+        return;
+    }
+    const float delta0 = __ldg(S.info + 6);
+    const float delta_min = delta0 * (1.f / 4096.f);
+    float t_in = VP_INF, t_out = -VP_INF;
+    {
+        float3 inv;
+        inv.x = 1.f / (fabsf(d.x) > 1e-30f ? d.x : copysignf(1e-30f, d.x));
+        inv.y = 1.f / (fabsf(d.y) > 1e-30f ? d.y : copysignf(1e-30f, d.y));
+        inv.z = 1.f / (fabsf(d.z) > 1e-30f ? d.z : copysignf(1e-30f, d.z));
+        const float3 lo = make_float3(__ldg(S.info), __ldg(S.info + 1), __ldg(S.info + 2));
+        const float3 hi = make_float3(__ldg(S.info + 3), __ldg(S.info + 4), __ldg(S.info + 5));
+        float ax = (lo.x - o0.x) * inv.x, bx = (hi.x - o0.x) * inv.x;
+        float ay = (lo.y - o0.y) * inv.y, by = (hi.y - o0.y) * inv.y;
+        float az = (lo.z - o0.z) * inv.z, bz = (hi.z - o0.z) * inv.z;
+        t_in = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+        t_out = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.000001f;
+        if (alive && !(t_in <= t_out)) { missed = true; alive = false; }
+        t_in = fmaxf(t_in * 0.999999f - 1e-6f, 0.f);
+    }
+    // warp-uniform interval start: where the first living ray enters the scene box
+    float t_start = alive ? t_in : VP_INF;
+    for (int off = 16; off; off >>= 1) t_start = fminf(t_start, __shfl_xor_sync(FULL, t_start, off));
+    float delta = delta0;
+    while (true) {
+        const unsigned am = __ballot_sync(FULL, alive);
+        if (!am) break;
+        const float inv_n = 1.f / (float)__popc(am);
+        const float t_lo = t_start - (1e-4f + 1e-5f * t_start);
+        const float t_end = t_start + delta;
+        if (alive) cn.passes++;
+        // ---- capsule around the living rays' segments [t_lo, t_end] ----
+        float3 P0 = make_float3(fmaf(d.x, t_lo, o0.x), fmaf(d.y, t_lo, o0.y), fmaf(d.z, t_lo, o0.z));
+        float3 P1 = make_float3(fmaf(d.x, t_end, o0.x), fmaf(d.y, t_end, o0.y), fmaf(d.z, t_end, o0.z));
+        float3 A = alive ? P0 : make_float3(0.f, 0.f, 0.f), B = alive ? P1 : make_float3(0.f, 0.f, 0.f);
+        for (int off = 16; off; off >>= 1) {
+            A.x += __shfl_xor_sync(FULL, A.x, off); A.y += __shfl_xor_sync(FULL, A.y, off); A.z += __shfl_xor_sync(FULL, A.z, off);
+            B.x += __shfl_xor_sync(FULL, B.x, off); B.y += __shfl_xor_sync(FULL, B.y, off); B.z += __shfl_xor_sync(FULL, B.z, off);
+        }
+        A.x *= inv_n; A.y *= inv_n; A.z *= inv_n; B.x *= inv_n; B.y *= inv_n; B.z *= inv_n;
+        float r = 0.f;
+        if (alive) {
+            float e0 = (P0.x - A.x) * (P0.x - A.x) + (P0.y - A.y) * (P0.y - A.y) + (P0.z - A.z) * (P0.z - A.z);
+            float e1 = (P1.x - B.x) * (P1.x - B.x) + (P1.y - B.y) * (P1.y - B.y) + (P1.z - B.z) * (P1.z - B.z);
+            r = sqrtf(fmaxf(e0, e1));
+        }
+        for (int off = 16; off; off >>= 1) r = fmaxf(r, __shfl_xor_sync(FULL, r, off));
+        r = r * 1.0001f + 1e-6f * (1.f + fabsf(A.x) + fabsf(A.y) + fabsf(A.z));
+        float3 Dx = make_float3(B.x - A.x, B.y - A.y, B.z - A.z), invD;
+        invD.x = 1.f / (fabsf(Dx.x) > 1e-30f ? Dx.x : copysignf(1e-30f, Dx.x));
+        invD.y = 1.f / (fabsf(Dx.y) > 1e-30f ? Dx.y : copysignf(1e-30f, Dx.y));
+        invD.z = 1.f / (fabsf(Dx.z) > 1e-30f ? Dx.z : copysignf(1e-30f, Dx.z));
+        const float3 AI = make_float3(A.x * invD.x, A.y * invD.y, A.z * invD.z);
+        // ---- phase 1 (cooperative): 32 queued nodes per step against the capsule ----
+        int qn = 1, tcn = 0;
+        bool overflow = false;
+        if (lane == 0) w_queue[0] = S.root;
+        __syncwarp();
+        while (qn > 0) {
+            const int take = qn < 32 ? qn : 32;
+            const int base = qn - take;
+            const int node = lane < take ? w_queue[base + lane] : -1;
+            qn = base;
+            __syncwarp();
+            bool iL = false, iR = false, lL = false, lR = false;
+            int left = 0, right = 0;
+            if (node >= 0) {
+                const float4 *nd = S.nodes + 4ll * node;
+                float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+                cn.nodes++;
+                const bool hl = slab(make_float3(n0.x - r, n0.y - r, n0.z - r), make_float3(n0.w + r, n1.x + r, n1.y + r), AI, invD, 0.f, 1.f);
+                const bool hr = slab(make_float3(n1.z - r, n1.w - r, n2.x - r), make_float3(n2.y + r, n2.z + r, n2.w + r), AI, invD, 0.f, 1.f);
+                left = __float_as_int(n3.x);
+                right = __float_as_int(n3.y);
+                iL = hl && left >= 0; lL = hl && left < 0;
+                iR = hr && right >= 0; lR = hr && right < 0;
+            }
+            const unsigned mIL = __ballot_sync(FULL, iL), mIR = __ballot_sync(FULL, iR);
+            const unsigned mLL = __ballot_sync(FULL, lL), mLR = __ballot_sync(FULL, lR);
+            const int nIL = __popc(mIL), nI = nIL + __popc(mIR), nLL = __popc(mLL), nL = nLL + __popc(mLR);
+            if (qn + nI > TILE_QCAP || tcn + nL > TILE_CCAP) { overflow = true; break; }
+            if (iL) w_queue[qn + __popc(mIL & lt)] = left;
+            if (iR) w_queue[qn + nIL + __popc(mIR & lt)] = right;
+            if (lL) w_cand[tcn + __popc(mLL & lt)] = ~left;
+            if (lR) w_cand[tcn + nLL + __popc(mLR & lt)] = ~right;
+            qn += nI;
+            tcn += nL;
+            __syncwarp();
+        }
+        __syncwarp();
+        // ---- phase 2: every lane tests the tile's candidates against its own ray ----
+        int n_h = 0;
+        bool lane_ovf = false;
+        if (!overflow) {
+            for (int k = 0; k < tcn; ++k) {
+                const int pos = w_cand[k];
+                float tn;
+                if (alive && fast_isect(S, pos, o0, d, tn) && tn > t_lo && tn <= t_end) {
+                    if (n_h < TILE_HIT_CAP) {
+                        s_id[n_h * TRACE_THREADS] = pos;
+                        s_t[n_h * TRACE_THREADS] = tn;
+                        ++n_h;
+                    } else lane_ovf = true;
+                }
+            }
+            if (alive) cn.candidates += tcn;
+        }
+        if (overflow || __any_sync(FULL, lane_ovf)) {
+            delta *= 0.5f;
+            if (delta < delta_min) {   // cannot be listed: the per-ray walker has the closest-hit fallback
+                bool m2 = false;
+                __syncwarp();
+                walk_ray(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit, t_start);
+                missed = missed || m2;
+                return;
+            }
+            continue;
+        }
+        // ---- phase 3: drain (per lane) ----
+        int found_sum = n_h;
+        for (int off = 16; off; off >>= 1) found_sum += __shfl_xor_sync(FULL, found_sum, off);
+        drain_list<TRACE_THREADS>(S, s_id, s_t, n_h, o, d, maxt, alive, missed, on_hit);
+        // ---- next interval (warp-uniform) ----
+        t_start = t_end;
+        const float avg = (float)found_sum * inv_n;
+        delta *= (found_sum == 0) ? 4.f : fminf(fmaxf((float)TARGET_HITS / avg, 0.5f), 2.f);
+        if (alive && t_start > t_out) { missed = true; alive = false; }
     }
 }
 
@@ -488,7 +669,7 @@ struct TraceArgs {
 };
 
 // ---- forward ----------------------------------------------------------------------------------
-template <int INTEG, int KERNEL, int D>
+template <int INTEG, int KERNEL, int D, bool TILE>
 __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(DevScene S, vp_params P, TraceArgs A)
 {
     extern __shared__ float4 smem_raw[];
@@ -514,8 +695,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
     if constexpr (INTEG == VP_INTEGRATOR_RF && D >= 0) sh_basis<(D >= 0 ? D : 0)>(d, Y);
     else Y[0] = 0.f;
 
-    walk_ray(S, s_id, s_t, o, o0, d, maxt, in_range, missed, cn,
-             [&](int pos, float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is) -> bool {
+    auto on_hit = [&](int pos, float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is) -> bool {
         float T;
         if constexpr (INTEG == VP_INTEGRATOR_RF) {
             RfEval e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
@@ -546,7 +726,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
         if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) return false;  // rf:173-174
         if (!(depth < P.max_depth)) return false;                             // rf:186
         return true;
-    });
+    };
+    if constexpr (TILE) walk_tile(S, reinterpret_cast<int *>(smem_raw), o, o0, d, maxt, in_range, missed, cn, on_hit);
+    else walk_ray(S, s_id, s_t, o, o0, d, maxt, in_range, missed, cn, on_hit);
 
     if (in_range) {
         if (INTEG == VP_INTEGRATOR_TOMO && missed && !(depth == 0 && P.hide_emitters)) {
@@ -748,7 +930,7 @@ __device__ __forceinline__ float tomo_adjoint_hit(const DevScene &S, const Trace
     return T;
 }
 
-template <int INTEG, int KERNEL, int D, bool REPLAY>
+template <int INTEG, int KERNEL, int D, bool REPLAY, bool TILE>
 __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_adjoint(DevScene S, vp_params P, TraceArgs A)
 {
     extern __shared__ float4 smem_raw[];
@@ -811,7 +993,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_adjoint(
         }
     } else {
         bool missed = false;
-        walk_ray(S, s_id, s_t, o, o0, d, maxt, alive, missed, cn, interact);
+        if constexpr (TILE) walk_tile(S, reinterpret_cast<int *>(smem_raw), o, o0, d, maxt, alive, missed, cn, interact);
+        else walk_ray(S, s_id, s_t, o, o0, d, maxt, alive, missed, cn, interact);
     }
     flush_counters(cn, A.stats);
 }
@@ -851,15 +1034,18 @@ template <int INTEG, int KERNEL, int D>
 void launch_forward(const DevScene &S, const vp_params &P, const TraceArgs &A, cudaStream_t st)
 {
     int64_t blocks = (A.R + TRACE_THREADS - 1) / TRACE_THREADS;
-    k_trace_forward<INTEG, KERNEL, D><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
+    // image-shaped launches walk the tree once per 8x4 tile (warp-cooperative); explicit ray batches per ray
+    if (P.image_width > 0) k_trace_forward<INTEG, KERNEL, D, true><<<(unsigned)blocks, TRACE_THREADS, TILE_SMEM, st>>>(S, P, A);
+    else k_trace_forward<INTEG, KERNEL, D, false><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
 }
 
 template <int INTEG, int KERNEL, int D>
 void launch_adjoint(const DevScene &S, const vp_params &P, const TraceArgs &A, cudaStream_t st)
 {
     int64_t blocks = (A.R + TRACE_THREADS - 1) / TRACE_THREADS;
-    if (A.rec_ids) k_trace_adjoint<INTEG, KERNEL, D, true><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
-    else k_trace_adjoint<INTEG, KERNEL, D, false><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
+    if (A.rec_ids) k_trace_adjoint<INTEG, KERNEL, D, true, false><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
+    else if (P.image_width > 0) k_trace_adjoint<INTEG, KERNEL, D, false, true><<<(unsigned)blocks, TRACE_THREADS, TILE_SMEM, st>>>(S, P, A);
+    else k_trace_adjoint<INTEG, KERNEL, D, false, false><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
 }
 
 template <bool FWD>
