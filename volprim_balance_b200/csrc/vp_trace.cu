@@ -30,22 +30,31 @@
 namespace {
 
 #ifndef VP_CAND_CAP
-#define VP_CAND_CAP 48
+#define VP_CAND_CAP 38   // 5 blocks x 38 KB of shared memory per SM
 #endif
 #ifndef VP_MIN_BLOCKS
-#define VP_MIN_BLOCKS 4
+#define VP_MIN_BLOCKS 5   // 96 registers / thread; measured best on cfg2 (4: -9%, 6: -1%, 8: -25%)
 #endif
 constexpr int CAND_CAP = VP_CAND_CAP;     // candidate / hit list entries per ray (shared memory: 8 B each)
-constexpr int TARGET_HITS = CAND_CAP / 4;  // the interval width adapts towards this many entries per interval
+#ifndef VP_TARGET_HITS
+#define VP_TARGET_HITS 10
+#endif
+constexpr int TARGET_HITS = VP_TARGET_HITS;  // the interval width adapts towards this many entries per interval
 constexpr int STACK_MAX = 96;    // LBVH depth bound: 63 Morton bits + index tie-break bits
 constexpr int TRACE_THREADS = 128;
 constexpr int NODE_SENTINEL = 0x7fffffff;
 constexpr size_t TRACE_SMEM = (size_t)CAND_CAP * TRACE_THREADS * 8;
 // warp-cooperative (tile) walker: per-lane hit lists + per-warp node queue and tile candidate list
-constexpr int TILE_HIT_CAP = 32;
-constexpr int TILE_QCAP = 640;
-constexpr int TILE_CCAP = 384;
+#ifndef VP_TILE_HIT_CAP
+#define VP_TILE_HIT_CAP 28
+#define VP_TILE_QCAP 512
+#define VP_TILE_CCAP 320
+#endif
+constexpr int TILE_HIT_CAP = VP_TILE_HIT_CAP;
+constexpr int TILE_QCAP = VP_TILE_QCAP;
+constexpr int TILE_CCAP = VP_TILE_CCAP;
 constexpr size_t TILE_SMEM = (size_t)TILE_HIT_CAP * TRACE_THREADS * 8 + (size_t)(TRACE_THREADS / 32) * (TILE_QCAP + TILE_CCAP) * 4;
+constexpr int TILE_FALLBACK_CAP = (int)(TILE_SMEM / (TRACE_THREADS * 8));  // per-ray lists that fit the same shared memory
 #define VP_INF __int_as_float(0x7f800000)
 
 struct Isect {
@@ -131,19 +140,30 @@ __device__ __forceinline__ bool slab(float3 lo, float3 hi, float3 oi, float3 inv
 
 // phase 3 of both walkers: hand the listed entries to on_hit in increasing distance.  Each entry is RE-EVALUATED
 // against the current, re-based origin `o` with the oracle's fixed-order arithmetic (quirk Q1, see file header).
+// phase 3 of both walkers hands the listed entries to on_hit in increasing distance; each entry is RE-EVALUATED
+// against the current, re-based origin `o` with the oracle's fixed-order arithmetic (quirk Q1, see file header).
+// sorted insert of (t, pos) into a per-lane list kept in increasing t (insertion sort: the lists are short)
+template <int STRIDE>
+__device__ __forceinline__ void list_insert(int *s_id, float *s_t, int n, float tn, int pos)
+{
+    int j = n;
+    while (j > 0) {
+        const float tp = s_t[(j - 1) * STRIDE];
+        if (!(tp > tn)) break;
+        s_t[j * STRIDE] = tp;
+        s_id[j * STRIDE] = s_id[(j - 1) * STRIDE];
+        --j;
+    }
+    s_t[j * STRIDE] = tn;
+    s_id[j * STRIDE] = pos;
+}
+
 template <int STRIDE, class OnHit>
 __device__ __forceinline__ void drain_list(const DevScene &S, const int *s_id, float *s_t, int n_found, const float3 &o,
                                            const float3 d, float maxt, bool &alive, bool &missed, OnHit &&on_hit)
 {
-    for (int taken = 0; alive && taken < n_found; ++taken) {
-        float bt = VP_INF;
-        int bk = 0;
-        for (int k = 0; k < n_found; ++k) {
-            float tk = s_t[k * STRIDE];
-            if (tk < bt) { bt = tk; bk = k; }
-        }
-        const int pos = s_id[bk * STRIDE];
-        s_t[bk * STRIDE] = VP_INF;
+    for (int k = 0; alive && k < n_found; ++k) {
+        const int pos = s_id[k * STRIDE];
         float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
         Mat3 Rm = vp_quat_to_matrix_rn(g2);
         Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
@@ -157,7 +177,7 @@ __device__ __forceinline__ void drain_list(const DevScene &S, const int *s_id, f
 // reference's order.  on_hit evaluates the primitive, advances the origin `o` (captured by the caller) and
 // returns false to terminate the ray.  WARP-CONVERGENT: all 32 lanes call it (lanes without a ray pass
 // alive = false).  s_id / s_t are this thread's columns of the shared candidate list (stride TRACE_THREADS).
-template <class OnHit>
+template <int CAP = CAND_CAP, class OnHit>
 __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_t, const float3 &o, const float3 o0,
                                          const float3 d, const float maxt, bool alive, bool &missed, Counters &cn,
                                          OnHit &&on_hit, const float t_begin = 0.f)
@@ -215,11 +235,11 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
             if (right >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.nodes + 4ll * right));
 #endif
             if (hl && left < 0) {
-                if (n_c < CAND_CAP) s_id[n_c * TRACE_THREADS] = ~left;
+                if (n_c < CAP) s_id[n_c * TRACE_THREADS] = ~left;
                 ++n_c;
             }
             if (hr && right < 0) {
-                if (n_c < CAND_CAP) s_id[n_c * TRACE_THREADS] = ~right;
+                if (n_c < CAP) s_id[n_c * TRACE_THREADS] = ~right;
                 ++n_c;
             }
             const bool vl = hl && left >= 0, vr = hr && right >= 0;
@@ -232,9 +252,9 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
                 node = vl ? left : (vr ? right : (sp > 0 ? top : NODE_SENTINEL));
                 sp -= (pop && sp > 0) ? 1 : 0;
             }
-            if (n_c > CAND_CAP) node = NODE_SENTINEL;                     // list overflow: abandon the interval
+            if (n_c > CAP) node = NODE_SENTINEL;                     // list overflow: abandon the interval
         }
-        if (n_c > CAND_CAP) { overflow = true; n_c = 0; }
+        if (n_c > CAP) { overflow = true; n_c = 0; }
         // closest-hit walk (fallback for lanes whose interval cannot be listed; rare)
         if (__any_sync(0xffffffffu, alive && closest_mode)) {
             int cnode = (alive && closest_mode) ? S.root : NODE_SENTINEL;
@@ -278,8 +298,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
                 if (S.root >= 0) ok = fast_isect(S, pos, o0, d, tn);
                 else { ok = true; tn = 1.f; }
                 if (ok && tn > t_lo && tn <= t_end) {
-                    s_id[n_h * TRACE_THREADS] = pos;
-                    s_t[n_h * TRACE_THREADS] = tn;
+                    list_insert<TRACE_THREADS>(s_id, s_t, n_h, tn, pos);   // n_h <= k: entry k is already read
                     ++n_h;
                 }
             }
@@ -336,13 +355,12 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
     int *w_queue = smem + 2 * TILE_HIT_CAP * TRACE_THREADS + (threadIdx.x >> 5) * (TILE_QCAP + TILE_CCAP);
     int *w_cand = w_queue + TILE_QCAP;
     int *fb_id = smem + threadIdx.x;
-    float *fb_t = reinterpret_cast<float *>(smem) + CAND_CAP * TRACE_THREADS + threadIdx.x;
-    static_assert(TILE_SMEM >= TRACE_SMEM, "the per-ray fallback lists must fit");
+    float *fb_t = reinterpret_cast<float *>(smem) + TILE_FALLBACK_CAP * TRACE_THREADS + threadIdx.x;
     const unsigned lt = (1u << lane) - 1u;
     missed = false;
     if (S.n <= 0) { missed = alive; return; }
     if (S.root < 0) {   // single primitive: nothing to share
-        walk_ray(S, fb_id, fb_t, o, o0, d, maxt, alive, missed, cn, on_hit);
+        walk_ray<TILE_FALLBACK_CAP>(S, fb_id, fb_t, o, o0, d, maxt, alive, missed, cn, on_hit);
         return;
     }
     const float delta0 = __ldg(S.info + 6);
@@ -434,18 +452,26 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         }
         __syncwarp();
         // ---- phase 2: every lane tests the tile's candidates against its own ray ----
+        // (warp-uniform loop, broadcast loads; four candidates per trip so that their loads overlap)
         int n_h = 0;
         bool lane_ovf = false;
         if (!overflow) {
-            for (int k = 0; k < tcn; ++k) {
-                const int pos = w_cand[k];
-                float tn;
-                if (alive && fast_isect(S, pos, o0, d, tn) && tn > t_lo && tn <= t_end) {
-                    if (n_h < TILE_HIT_CAP) {
-                        s_id[n_h * TRACE_THREADS] = pos;
-                        s_t[n_h * TRACE_THREADS] = tn;
-                        ++n_h;
-                    } else lane_ovf = true;
+            for (int k0 = 0; k0 < tcn; k0 += 4) {
+                int pos[4];
+                float tn[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pos[u] = w_cand[k0 + u < tcn ? k0 + u : k0];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ok[u] = fast_isect(S, pos[u], o0, d, tn[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (alive && k0 + u < tcn && ok[u] && tn[u] > t_lo && tn[u] <= t_end) {
+                        if (n_h < TILE_HIT_CAP) {
+                            list_insert<TRACE_THREADS>(s_id, s_t, n_h, tn[u], pos[u]);
+                            ++n_h;
+                        } else lane_ovf = true;
+                    }
                 }
             }
             if (alive) cn.candidates += tcn;
@@ -455,7 +481,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
             if (delta < delta_min) {   // cannot be listed: the per-ray walker has the closest-hit fallback
                 bool m2 = false;
                 __syncwarp();
-                walk_ray(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit, t_start);
+                walk_ray<TILE_FALLBACK_CAP>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit, t_start);
                 missed = missed || m2;
                 return;
             }
@@ -546,18 +572,21 @@ template <int KERNEL>
 __device__ __forceinline__ RfEval rf_eval(float3 o, float3 d, float4 g0, float4 g1, const Mat3 &R, const Isect &is)
 {
     RfEval e;
-    float3 oo = make_float3(is.ro.x / g1.x, is.ro.y / g1.y, is.ro.z / g1.z);
-    float3 dd = make_float3(is.rd.x / g1.x, is.rd.y / g1.y, is.rd.z / g1.z);
-    float od = vp_dot_rn(oo, dd), dd2 = vp_dot_rn(dd, dd);
+    // (value path: reciprocal scales instead of nine IEEE divisions; agrees with the oracle to a few ulp)
+    const float isx = 1.f / g1.x, isy = 1.f / g1.y, isz = 1.f / g1.z;
+    float3 oo = make_float3(is.ro.x * isx, is.ro.y * isy, is.ro.z * isz);
+    float3 dd = make_float3(is.rd.x * isx, is.rd.y * isy, is.rd.z * isz);
+    float od = oo.x * dd.x + oo.y * dd.y + oo.z * dd.z, dd2 = dd.x * dd.x + dd.y * dd.y + dd.z * dd.z;
     float tp = -od / dd2;
     e.pp = make_float3(fmaf(d.x, tp, o.x), fmaf(d.y, tp, o.y), fmaf(d.z, tp, o.z));
     float3 v = make_float3(e.pp.x - g0.x, e.pp.y - g0.y, e.pp.z - g0.z);
     float3 w = vp_rot_t_mul_rn(R, v);
     if (KERNEL == VP_KERNEL_GAUSSIAN) {
-        float q = (w.x * w.x) / (g1.x * g1.x) + (w.y * w.y) / (g1.y * g1.y) + (w.z * w.z) / (g1.z * g1.z);
+        float ux = w.x * isx, uy = w.y * isy, uz = w.z * isz;
+        float q = ux * ux + uy * uy + uz * uz;
         e.G = expf(-0.5f * q);
     } else {
-        float ux = w.x / (g1.x * 3.f), uy = w.y / (g1.y * 3.f), uz = w.z / (g1.z * 3.f);
+        float ux = w.x * isx * (1.f / 3.f), uy = w.y * isy * (1.f / 3.f), uz = w.z * isz * (1.f / 3.f);
         float dist = sqrtf(ux * ux + uy * uy + uz * uz);
         e.G = fmaxf(0.75f * (1.f - dist * dist), 0.f);
     }
