@@ -140,6 +140,20 @@ __device__ __forceinline__ bool slab(float3 lo, float3 hi, float3 oi, float3 inv
 
 // phase 3 of both walkers: hand the listed entries to on_hit in increasing distance.  Each entry is RE-EVALUATED
 // against the current, re-based origin `o` with the oracle's fixed-order arithmetic (quirk Q1, see file header).
+// L1 prefetch of everything the evaluation of primitive `pos` will read (3 geometry records + the SH block):
+// issued one entry ahead so that the next hit's gathers overlap the current hit's arithmetic.
+__device__ __forceinline__ void prefetch_prim(const DevScene &S, int pos)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.geo0 + pos));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.geo1 + pos));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.geo2 + pos));
+    if (S.sh_stride4 > 0) {
+        const float4 *f = S.sh4 + (size_t)pos * S.sh_stride4;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(f));
+        if (S.sh_stride4 > 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(f + 8));
+    }
+}
+
 // phase 3 of both walkers hands the listed entries to on_hit in increasing distance; each entry is RE-EVALUATED
 // against the current, re-based origin `o` with the oracle's fixed-order arithmetic (quirk Q1, see file header).
 // sorted insert of (t, pos) into a per-lane list kept in increasing t (insertion sort: the lists are short)
@@ -162,8 +176,10 @@ template <int STRIDE, class OnHit>
 __device__ __forceinline__ void drain_list(const DevScene &S, const int *s_id, float *s_t, int n_found, const float3 &o,
                                            const float3 d, float maxt, bool &alive, bool &missed, OnHit &&on_hit)
 {
+    if (alive && n_found > 0) prefetch_prim(S, s_id[0]);
     for (int k = 0; alive && k < n_found; ++k) {
         const int pos = s_id[k * STRIDE];
+        if (k + 1 < n_found) prefetch_prim(S, s_id[(k + 1) * STRIDE]);
         float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
         Mat3 Rm = vp_quat_to_matrix_rn(g2);
         Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
@@ -959,8 +975,11 @@ __device__ __forceinline__ float tomo_adjoint_hit(const DevScene &S, const Trace
     return T;
 }
 
+#ifndef VP_REPLAY_BLOCKS
+#define VP_REPLAY_BLOCKS 8   // the replay adjoint uses no shared memory; bound by reduction throughput, not occupancy
+#endif
 template <int INTEG, int KERNEL, int D, bool REPLAY, bool TILE>
-__global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_adjoint(DevScene S, vp_params P, TraceArgs A)
+__global__ void __launch_bounds__(TRACE_THREADS, REPLAY ? VP_REPLAY_BLOCKS : VP_MIN_BLOCKS) k_trace_adjoint(DevScene S, vp_params P, TraceArgs A)
 {
     extern __shared__ float4 smem_raw[];
     int *s_id = reinterpret_cast<int *>(smem_raw) + threadIdx.x;
@@ -1010,10 +1029,17 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_adjoint(
         if (alive) {
             uint32_t n = A.rec_counts[r];
             if (n > (uint32_t)A.cap) n = (uint32_t)A.cap;
+            // software pipeline: the id -> position -> records chain of hit k+1 is started during hit k
+            int orig_next = n > 0 ? A.rec_ids[r * A.rs] : -1;
+            int pos_next = orig_next >= 0 ? __ldg(S.inv_perm + orig_next) : 0;
+            if (orig_next >= 0) prefetch_prim(S, pos_next);
             for (uint32_t k = 0; k < n; ++k) {
-                int orig = A.rec_ids[r * A.rs + k * A.hs];
+                const int orig = orig_next;
                 if (orig < 0) break;
-                int pos = __ldg(S.inv_perm + orig);
+                const int pos = pos_next;
+                orig_next = (k + 1 < n) ? A.rec_ids[r * A.rs + (k + 1) * A.hs] : -1;
+                pos_next = orig_next >= 0 ? __ldg(S.inv_perm + orig_next) : 0;
+                if (orig_next >= 0) prefetch_prim(S, pos_next);
                 float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
                 Mat3 Rm = vp_quat_to_matrix_rn(g2);
                 Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
