@@ -114,8 +114,8 @@ def cpu_reference_sample(wl, cloud, view, stride=8, threads=None, repeats=1):
     pixel subsample (x, y) % stride == stride/2 of one view.  Returns (Mrays/s, cores, description)."""
     from oracle import oracle as O
     from volprim_balance_b200 import synthetic
-    if threads:
-        O.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1: ask for every host core this process may use
+    O.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = O.num_threads()
     cam = synthetic.ring_camera(view, wl["views"], wl["W"], wl["H"])
     o, d, mt = synthetic.camera_rays(cam)
@@ -255,6 +255,27 @@ def run_ours(args, wl, rank, world, local_rank):
     peak, peak_src = measured_peak()
     mean_hits = sum(hits_per_view[my_view(s)] for s in range(args.steps)) / (args.steps * R)
 
+    # ---- forward (recording hit lists) + replayed PRB adjoint, ms / view (second half of BASELINE's metric) ----------
+    dL = torch.randn((R, 3), device=dev) * (1.0 / R)
+    gbuf = (torch.zeros(cloud.n * 10, device=dev), torch.zeros(cloud.n, device=dev),
+            torch.zeros(cloud.n * cloud.sh_coeffs.shape[1], device=dev))
+
+    def step_fwd_adj(step):
+        o, d, mt = rays[my_view(step)]
+        r = acc.trace_forward(params, o, d, mt, record_cap=128)
+        acc.trace_adjoint(params, o, d, mt, dL, r.rgb, r.hit_ids, r.nhits, out=gbuf)
+
+    step_fwd_adj(0)
+    barrier()
+    n_fa = min(args.steps, 4)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for s in range(n_fa):
+        step_fwd_adj(s)
+    f1.record()
+    barrier()
+    fwd_adj_ms = f0.elapsed_time(f1) / n_fa
+
     # ---- end to end through the public API: render() + image to pinned host memory ---------------------
     host_img = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
     for s in range(2):
@@ -305,6 +326,7 @@ def run_ours(args, wl, rank, world, local_rank):
                      "algorithmic_bytes_per_launch": sum(algo_bytes) / len(algo_bytes),
                      "kernel_ms": sum(kern_ms) / len(kern_ms), "peak_source": peak_src},
         "primitive_evals_per_s": mean_hits * R * args.steps * world / (total_ms * 1e-3),
+        "fwd_adjoint_ms_per_view": fwd_adj_ms,
     }
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
