@@ -347,6 +347,55 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
     }
 }
 
+// Capsule around the living lanes' ray segments [t0, t1]: mean segment A -> B and the largest deviation r of any
+// lane's segment end points from it (distance between two linear motions is convex, so the ends bound the whole
+// segment).  Boxes inflated by r and tested against the axis segment (parameter in [0, 1]) are a conservative cull.
+struct Capsule {
+    float3 AI, invD;
+    float r;
+};
+__device__ __forceinline__ Capsule tile_capsule(bool alive, unsigned am, float3 o0, float3 d, float t0, float t1)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const float inv_n = 1.f / (float)__popc(am);
+    float3 P0 = make_float3(fmaf(d.x, t0, o0.x), fmaf(d.y, t0, o0.y), fmaf(d.z, t0, o0.z));
+    float3 P1 = make_float3(fmaf(d.x, t1, o0.x), fmaf(d.y, t1, o0.y), fmaf(d.z, t1, o0.z));
+    float3 A = alive ? P0 : make_float3(0.f, 0.f, 0.f), B = alive ? P1 : make_float3(0.f, 0.f, 0.f);
+    for (int off = 16; off; off >>= 1) {
+        A.x += __shfl_xor_sync(FULL, A.x, off); A.y += __shfl_xor_sync(FULL, A.y, off); A.z += __shfl_xor_sync(FULL, A.z, off);
+        B.x += __shfl_xor_sync(FULL, B.x, off); B.y += __shfl_xor_sync(FULL, B.y, off); B.z += __shfl_xor_sync(FULL, B.z, off);
+    }
+    A.x *= inv_n; A.y *= inv_n; A.z *= inv_n; B.x *= inv_n; B.y *= inv_n; B.z *= inv_n;
+    float r = 0.f;
+    if (alive) {
+        float e0 = (P0.x - A.x) * (P0.x - A.x) + (P0.y - A.y) * (P0.y - A.y) + (P0.z - A.z) * (P0.z - A.z);
+        float e1 = (P1.x - B.x) * (P1.x - B.x) + (P1.y - B.y) * (P1.y - B.y) + (P1.z - B.z) * (P1.z - B.z);
+        r = sqrtf(fmaxf(e0, e1));
+    }
+    for (int off = 16; off; off >>= 1) r = fmaxf(r, __shfl_xor_sync(FULL, r, off));
+    Capsule c;
+    c.r = r * 1.0001f + 1e-6f * (1.f + fabsf(A.x) + fabsf(A.y) + fabsf(A.z));
+    float3 Dx = make_float3(B.x - A.x, B.y - A.y, B.z - A.z);
+    c.invD.x = 1.f / (fabsf(Dx.x) > 1e-30f ? Dx.x : copysignf(1e-30f, Dx.x));
+    c.invD.y = 1.f / (fabsf(Dx.y) > 1e-30f ? Dx.y : copysignf(1e-30f, Dx.y));
+    c.invD.z = 1.f / (fabsf(Dx.z) > 1e-30f ? Dx.z : copysignf(1e-30f, Dx.z));
+    c.AI = make_float3(A.x * c.invD.x, A.y * c.invD.y, A.z * c.invD.z);
+    return c;
+}
+
+// child boxes of one node against a capsule
+__device__ __forceinline__ void capsule_children(const DevScene &S, int node, const Capsule &c, bool &hl, bool &hr,
+                                                 int &left, int &right)
+{
+    const float4 *nd = S.nodes + 4ll * node;
+    float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+    const float r = c.r;
+    hl = slab(make_float3(n0.x - r, n0.y - r, n0.z - r), make_float3(n0.w + r, n1.x + r, n1.y + r), c.AI, c.invD, 0.f, 1.f);
+    hr = slab(make_float3(n1.z - r, n1.w - r, n2.x - r), make_float3(n2.y + r, n2.z + r, n2.w + r), c.AI, c.invD, 0.f, 1.f);
+    left = __float_as_int(n3.x);
+    right = __float_as_int(n3.y);
+}
+
 // Warp-cooperative walker for COHERENT rays (the 32 lanes of a warp are an 8x4 pixel tile).
 //
 // The per-ray walker spends three quarters of its time in ~600 DEPENDENT node visits per ray.  Here the warp walks
@@ -401,6 +450,37 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
     float t_start = alive ? t_in : VP_INF;
     for (int off = 16; off; off >>= 1) t_start = fminf(t_start, __shfl_xor_sync(FULL, t_start, off));
     float delta = delta0;
+    // ---- tile root set: the subtrees the tile's rays can reach at all (capsule over the whole remaining range).
+    // Every interval starts its walk from these <= 32 nodes (one per lane, in a register) instead of re-descending
+    // from the root with a nearly empty queue. ----
+    int rs_node = lane == 0 ? S.root : -1, rs_n = 1;
+    {
+        const unsigned am0 = __ballot_sync(FULL, alive);
+        if (!am0) return;
+        float t_far = alive ? t_out : -VP_INF;
+        for (int off = 16; off; off >>= 1) t_far = fmaxf(t_far, __shfl_xor_sync(FULL, t_far, off));
+        const Capsule cf = tile_capsule(alive, am0, o0, d, fmaxf(t_start - 1e-3f, 0.f), t_far);
+        for (int iter = 0; iter < 12 && rs_n <= 16; ++iter) {
+            bool hl = false, hr = false;
+            int left = 0, right = 0;
+            if (rs_node >= 0) capsule_children(S, rs_node, cf, hl, hr, left, right);
+            const bool leaf_hit = (hl && left < 0) || (hr && right < 0);
+            const bool expand = rs_node >= 0 && !leaf_hit;     // a node with a reachable leaf child stays as it is
+            if (!__any_sync(FULL, expand)) break;
+            const int c0 = expand ? (hl ? left : (hr ? right : -1)) : rs_node;
+            const int c1 = (expand && hl && hr) ? right : -1;
+            const unsigned m0 = __ballot_sync(FULL, c0 >= 0), m1 = __ballot_sync(FULL, c1 >= 0);
+            const int n0 = __popc(m0), n1 = __popc(m1);
+            if (n0 + n1 > 32) break;
+            __syncwarp();
+            if (c0 >= 0) w_queue[__popc(m0 & lt)] = c0;
+            if (c1 >= 0) w_queue[n0 + __popc(m1 & lt)] = c1;
+            __syncwarp();
+            rs_n = n0 + n1;
+            rs_node = lane < rs_n ? w_queue[lane] : -1;
+            __syncwarp();
+        }
+    }
     while (true) {
         const unsigned am = __ballot_sync(FULL, alive);
         if (!am) break;
@@ -408,32 +488,11 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         const float t_lo = t_start - (1e-4f + 1e-5f * t_start);
         const float t_end = t_start + delta;
         if (alive) cn.passes++;
-        // ---- capsule around the living rays' segments [t_lo, t_end] ----
-        float3 P0 = make_float3(fmaf(d.x, t_lo, o0.x), fmaf(d.y, t_lo, o0.y), fmaf(d.z, t_lo, o0.z));
-        float3 P1 = make_float3(fmaf(d.x, t_end, o0.x), fmaf(d.y, t_end, o0.y), fmaf(d.z, t_end, o0.z));
-        float3 A = alive ? P0 : make_float3(0.f, 0.f, 0.f), B = alive ? P1 : make_float3(0.f, 0.f, 0.f);
-        for (int off = 16; off; off >>= 1) {
-            A.x += __shfl_xor_sync(FULL, A.x, off); A.y += __shfl_xor_sync(FULL, A.y, off); A.z += __shfl_xor_sync(FULL, A.z, off);
-            B.x += __shfl_xor_sync(FULL, B.x, off); B.y += __shfl_xor_sync(FULL, B.y, off); B.z += __shfl_xor_sync(FULL, B.z, off);
-        }
-        A.x *= inv_n; A.y *= inv_n; A.z *= inv_n; B.x *= inv_n; B.y *= inv_n; B.z *= inv_n;
-        float r = 0.f;
-        if (alive) {
-            float e0 = (P0.x - A.x) * (P0.x - A.x) + (P0.y - A.y) * (P0.y - A.y) + (P0.z - A.z) * (P0.z - A.z);
-            float e1 = (P1.x - B.x) * (P1.x - B.x) + (P1.y - B.y) * (P1.y - B.y) + (P1.z - B.z) * (P1.z - B.z);
-            r = sqrtf(fmaxf(e0, e1));
-        }
-        for (int off = 16; off; off >>= 1) r = fmaxf(r, __shfl_xor_sync(FULL, r, off));
-        r = r * 1.0001f + 1e-6f * (1.f + fabsf(A.x) + fabsf(A.y) + fabsf(A.z));
-        float3 Dx = make_float3(B.x - A.x, B.y - A.y, B.z - A.z), invD;
-        invD.x = 1.f / (fabsf(Dx.x) > 1e-30f ? Dx.x : copysignf(1e-30f, Dx.x));
-        invD.y = 1.f / (fabsf(Dx.y) > 1e-30f ? Dx.y : copysignf(1e-30f, Dx.y));
-        invD.z = 1.f / (fabsf(Dx.z) > 1e-30f ? Dx.z : copysignf(1e-30f, Dx.z));
-        const float3 AI = make_float3(A.x * invD.x, A.y * invD.y, A.z * invD.z);
-        // ---- phase 1 (cooperative): 32 queued nodes per step against the capsule ----
-        int qn = 1, tcn = 0;
+        const Capsule cap = tile_capsule(alive, am, o0, d, t_lo, t_end);
+        // ---- phase 1 (cooperative): 32 queued nodes per step against the interval's capsule ----
+        int qn = rs_n, tcn = 0;
         bool overflow = false;
-        if (lane == 0) w_queue[0] = S.root;
+        if (lane < rs_n) w_queue[lane] = rs_node;
         __syncwarp();
         while (qn > 0) {
             const int take = qn < 32 ? qn : 32;
@@ -444,13 +503,9 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
             bool iL = false, iR = false, lL = false, lR = false;
             int left = 0, right = 0;
             if (node >= 0) {
-                const float4 *nd = S.nodes + 4ll * node;
-                float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+                bool hl, hr;
+                capsule_children(S, node, cap, hl, hr, left, right);
                 cn.nodes++;
-                const bool hl = slab(make_float3(n0.x - r, n0.y - r, n0.z - r), make_float3(n0.w + r, n1.x + r, n1.y + r), AI, invD, 0.f, 1.f);
-                const bool hr = slab(make_float3(n1.z - r, n1.w - r, n2.x - r), make_float3(n2.y + r, n2.z + r, n2.w + r), AI, invD, 0.f, 1.f);
-                left = __float_as_int(n3.x);
-                right = __float_as_int(n3.y);
                 iL = hl && left >= 0; lL = hl && left < 0;
                 iR = hr && right >= 0; lR = hr && right < 0;
             }
