@@ -171,3 +171,22 @@ def test_dense_overlap_falls_back_to_closest_hit_search():
         st = compare_forward(res, ref, 320, max_fragile_frac=0.02)
         assert ref.nhits.max() > 100
         print(st)
+
+
+def test_tile_walker_fallback_does_not_disturb_neighbour_warps():
+    """Coarse image over a dense cloud: tiles are wide, their candidate lists overflow and single warps hand over to
+    the per-ray walker while the other warps of the block keep using their shared-memory queues (regression: the
+    fallback lists once overlapped the neighbours' queues -> illegal address at 2M primitives)."""
+    n = 400_000
+    cloud = synthetic.make_cloud(n, 0.0025, seed=2, sh_degree=0)
+    o, d, mt = _rays(view=0, w=64, h=32)
+    acc = gpu_scene(cloud)
+    pt, op = make_params(0, 0, max_depth=128, image=(64, 32))
+    pr, _ = make_params(0, 0, max_depth=128)
+    to, td, tm = torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt)
+    a = acc.trace_forward(pt, to, td, tm, record_cap=128)
+    b = acc.trace_forward(pr, to, td, tm, record_cap=128)
+    same = (a.hit_ids == b.hit_ids).all(0)
+    assert float(same.float().mean()) > 0.995
+    ref = oracle_scene(cloud).forward(op, o, d, mt, cap=128, fragility=True)
+    print(compare_forward(a, ref, 128))

@@ -233,7 +233,7 @@ __global__ void k_gather_soa(const float *__restrict__ data10, const float *__re
                              int32_t *__restrict__ inv_perm, float4 *__restrict__ leaf_lo, float4 *__restrict__ leaf_hi)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    float area = 0.f;
+    float area = 0.f, half = 0.f;
     if (p < n) {
     int j = (int)order[p];
     const float *rec = data10 + 10ll * j;
@@ -301,9 +301,12 @@ __global__ void k_gather_soa(const float *__restrict__ data10, const float *__re
     float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
     if (isfinite(ex) && isfinite(ey) && isfinite(ez) && ex > 0.f && ey > 0.f && ez > 0.f)
         area = 0.5f * (ex * ey + ey * ez + ez * ex);
+        half = (ex + ey + ez) * (1.f / 6.f);
     }
     for (int off = 16; off; off >>= 1) area += __shfl_xor_sync(0xffffffffu, area, off);
     if ((threadIdx.x & 31) == 0 && area > 0.f) atomicAdd(info + 7, area);
+    for (int off = 16; off; off >>= 1) half += __shfl_xor_sync(0xffffffffu, half, off);
+    if ((threadIdx.x & 31) == 0 && half > 0.f) atomicAdd(info + 8, half);
 }
 
 // scene box (union of the root's child boxes, or the single leaf) and the initial interval width
@@ -332,6 +335,7 @@ __global__ void k_scene_info(int n, const float *__restrict__ nodes, const float
     delta0 = fminf(delta0, fmaxf(diag, 1e-20f));
     for (int a = 0; a < 3; ++a) { info[a] = lo[a]; info[3 + a] = hi[a]; }
     info[6] = delta0;
+    info[8] = info[8] / (float)n;   // mean half-extent of a leaf box (tile-vs-per-ray walker heuristic)
 }
 
 // 5. Karras 2012
@@ -445,7 +449,7 @@ int vp_build_impl(vp_ctx *ctx, bool refit_only, cudaStream_t st)
     if ((rc = vp_ensure(ctx, ctx->geo2, sizeof(float4) * n))) return rc;
     if ((rc = vp_ensure(ctx, ctx->sh4, sizeof(float4) * (size_t)n * (sh_stride4 > 0 ? sh_stride4 : 1)))) return rc;
     if ((rc = vp_ensure(ctx, ctx->xf, sizeof(float4) * 3 * (size_t)n))) return rc;
-    if ((rc = vp_ensure(ctx, ctx->info, sizeof(float) * 8))) return rc;
+    if ((rc = vp_ensure(ctx, ctx->info, sizeof(float) * 12))) return rc;
     if ((rc = vp_ensure(ctx, ctx->nodes, sizeof(float) * 16 * (size_t)(n > 1 ? n - 1 : 1)))) return rc;
     if ((rc = vp_ensure(ctx, ctx->perm, sizeof(int32_t) * n))) return rc;
     if ((rc = vp_ensure(ctx, ctx->inv_perm, sizeof(int32_t) * n))) return rc;
@@ -489,7 +493,7 @@ int vp_build_impl(vp_ctx *ctx, bool refit_only, cudaStream_t st)
         order = (const uint32_t *)ctx->perm.ptr;  // perm holds the same values (int32 >= 0)
     }
 
-    VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->info.ptr, 0, sizeof(float) * 8, st));
+    VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->info.ptr, 0, sizeof(float) * 12, st));
     k_gather_soa<<<cdiv(n, B), B, 0, st>>>(data10, attr, sh, n, ctx->sh_floats, sh_stride4, ctx->extent, order,
                                            (float4 *)ctx->geo0.ptr, (float4 *)ctx->geo1.ptr, (float4 *)ctx->geo2.ptr,
                                            (float4 *)ctx->sh4.ptr, (float4 *)ctx->xf.ptr, (float *)ctx->info.ptr,

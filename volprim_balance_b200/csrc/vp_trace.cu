@@ -54,8 +54,14 @@ constexpr int TILE_HIT_CAP = VP_TILE_HIT_CAP;
 constexpr int TILE_QCAP = VP_TILE_QCAP;
 constexpr int TILE_CCAP = VP_TILE_CCAP;
 constexpr size_t TILE_SMEM = (size_t)TILE_HIT_CAP * TRACE_THREADS * 8 + (size_t)(TRACE_THREADS / 32) * (TILE_QCAP + TILE_CCAP) * 4;
-constexpr int TILE_FALLBACK_CAP = (int)(TILE_SMEM / (TRACE_THREADS * 8));  // per-ray lists that fit the same shared memory
+constexpr int TILE_FALLBACK_CAP = TILE_HIT_CAP;  // the per-ray fallback may only touch the warp's OWN list columns
 #define VP_INF __int_as_float(0x7f800000)
+#ifdef VP_DEBUG_CHECKS   // bounds checks for debugging builds (compute-sanitizer is not available on the GPU pool)
+#include <cstdio>
+#define VP_CHECK(cond, code, a, b) do { if (!(cond)) printf("VP_CHECK %d failed: %d %d (block %d thread %d)\n", code, (int)(a), (int)(b), blockIdx.x, threadIdx.x); } while (0)
+#else
+#define VP_CHECK(cond, code, a, b) do { } while (0)
+#endif
 
 struct Isect {
     bool valid;
@@ -104,6 +110,7 @@ struct Counters {
 // (slightly negative discriminants pass) because the drain phase repeats the test exactly.
 __device__ __forceinline__ bool fast_isect(const DevScene &S, int pos, float3 o, float3 d, float &tn)
 {
+    VP_CHECK(pos >= 0 && pos < S.n, 1, pos, S.n);
     const float4 *x = S.xf + 3ll * pos;
     float4 r0 = __ldg(x), r1 = __ldg(x + 1), r2 = __ldg(x + 2);
     float3 v = make_float3(o.x - r0.w, o.y - r1.w, o.z - r2.w);
@@ -160,6 +167,7 @@ __device__ __forceinline__ void prefetch_prim(const DevScene &S, int pos)
 template <int STRIDE>
 __device__ __forceinline__ void list_insert(int *s_id, float *s_t, int n, float tn, int pos)
 {
+    VP_CHECK(n >= 0 && n < 64, 4, n, pos);
     int j = n;
     while (j > 0) {
         const float tp = s_t[(j - 1) * STRIDE];
@@ -176,9 +184,11 @@ template <int STRIDE, class OnHit>
 __device__ __forceinline__ void drain_list(const DevScene &S, const int *s_id, float *s_t, int n_found, const float3 &o,
                                            const float3 d, float maxt, bool &alive, bool &missed, OnHit &&on_hit)
 {
+    VP_CHECK(n_found >= 0 && n_found <= 64, 5, n_found, 0);
     if (alive && n_found > 0) prefetch_prim(S, s_id[0]);
     for (int k = 0; alive && k < n_found; ++k) {
         const int pos = s_id[k * STRIDE];
+        VP_CHECK(pos >= 0 && pos < S.n, 6, pos, k);
         if (k + 1 < n_found) prefetch_prim(S, s_id[(k + 1) * STRIDE]);
         float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
         Mat3 Rm = vp_quat_to_matrix_rn(g2);
@@ -239,6 +249,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
         int sp = 0;
         if (alive && S.root < 0) { s_id[0] = ~S.root; n_c = 1; }       // single-primitive scene
         while (node != NODE_SENTINEL) {
+            VP_CHECK(node >= 0 && node < S.n - 1, 7, node, sp);
             const float4 *nd = S.nodes + 4ll * node;
             float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
             const int top = stack[sp > 0 ? sp - 1 : 0];                   // speculative: used only on a pop
@@ -387,6 +398,7 @@ __device__ __forceinline__ Capsule tile_capsule(bool alive, unsigned am, float3 
 __device__ __forceinline__ void capsule_children(const DevScene &S, int node, const Capsule &c, bool &hl, bool &hr,
                                                  int &left, int &right)
 {
+    VP_CHECK(node >= 0 && node < S.n - 1, 2, node, S.n);
     const float4 *nd = S.nodes + 4ll * node;
     float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
     const float r = c.r;
@@ -413,14 +425,15 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
 {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    // shared memory: [hit ids 32 x 128][hit t 32 x 128][per warp: node queue, tile candidates]; the per-ray
-    // fallback re-uses the same 48 KB as [ids 48 x 128][t 48 x 128]
+    // shared memory: [hit ids CAP x 128][hit t CAP x 128][per warp: node queue, tile candidates].  The per-ray
+    // fallback runs per WARP while the other warps of the block keep walking, so it re-uses exactly this warp's
+    // list columns (a wider layout would overwrite the neighbours' queues -- found the hard way)
     int *s_id = smem + threadIdx.x;
     float *s_t = reinterpret_cast<float *>(smem) + TILE_HIT_CAP * TRACE_THREADS + threadIdx.x;
     int *w_queue = smem + 2 * TILE_HIT_CAP * TRACE_THREADS + (threadIdx.x >> 5) * (TILE_QCAP + TILE_CCAP);
     int *w_cand = w_queue + TILE_QCAP;
-    int *fb_id = smem + threadIdx.x;
-    float *fb_t = reinterpret_cast<float *>(smem) + TILE_FALLBACK_CAP * TRACE_THREADS + threadIdx.x;
+    int *fb_id = s_id;
+    float *fb_t = s_t;
     const unsigned lt = (1u << lane) - 1u;
     missed = false;
     if (S.n <= 0) { missed = alive; return; }
@@ -459,6 +472,18 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         if (!am0) return;
         float t_far = alive ? t_out : -VP_INF;
         for (int off = 16; off; off >>= 1) t_far = fmaxf(t_far, __shfl_xor_sync(FULL, t_far, off));
+        // A tile much wider than the primitives (coarse images, incoherent "tiles") would list several times more
+        // candidates per lane than a ray of its own needs: cost grows like (1 + r / h)^2 with r the capsule radius
+        // and h the mean leaf half-extent.  Beyond r = 2 h (9 x the candidates) every lane walks for itself.
+        {
+            const Capsule c0 = tile_capsule(alive, am0, o0, d, t_start, t_start + delta0);
+            if (c0.r > 2.f * __ldg(S.info + 8)) {
+                bool m2 = false;   // lanes that missed the scene box keep their `missed`
+                walk_ray<TILE_FALLBACK_CAP>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit);
+                missed = missed || m2;
+                return;
+            }
+        }
         const Capsule cf = tile_capsule(alive, am0, o0, d, fmaxf(t_start - 1e-3f, 0.f), t_far);
         for (int iter = 0; iter < 12 && rs_n <= 16; ++iter) {
             bool hl = false, hr = false;
@@ -513,6 +538,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
             const unsigned mLL = __ballot_sync(FULL, lL), mLR = __ballot_sync(FULL, lR);
             const int nIL = __popc(mIL), nI = nIL + __popc(mIR), nLL = __popc(mLL), nL = nLL + __popc(mLR);
             if (qn + nI > TILE_QCAP || tcn + nL > TILE_CCAP) { overflow = true; break; }
+            VP_CHECK(qn >= 0 && qn + nI <= TILE_QCAP && tcn + nL <= TILE_CCAP, 3, qn + nI, tcn + nL);
             if (iL) w_queue[qn + __popc(mIL & lt)] = left;
             if (iR) w_queue[qn + nIL + __popc(mIR & lt)] = right;
             if (lL) w_cand[tcn + __popc(mLL & lt)] = ~left;
@@ -565,7 +591,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         // ---- next interval (warp-uniform) ----
         t_start = t_end;
         const float avg = (float)found_sum * inv_n;
-        delta *= (found_sum == 0) ? 4.f : fminf(fmaxf((float)TARGET_HITS / avg, 0.5f), 2.f);
+        delta *= (avg < 0.25f * (float)TARGET_HITS) ? 4.f : fminf(fmaxf((float)TARGET_HITS / avg, 0.5f), 2.f);
         if (alive && t_start > t_out) { missed = true; alive = false; }
     }
 }
