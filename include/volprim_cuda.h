@@ -129,6 +129,15 @@ VP_API int vp_raygen_perspective(vp_ctx *ctx, const vp_camera *cam, int32_t spp,
 /* Copy the work counters of the most recent trace call to the host (synchronises `stream`). */
 VP_API int vp_get_stats(vp_ctx *ctx, vp_stats *host_out, void *stream);
 
+/* BoundedAdam.step for one parameter tensor, fused into one pass (volprim/optimizers.py:72-146; non-uniform,
+ * unmasked variant -- the one the reference's examples use).  Host scalars are doubles like the reference's Python
+ * floats (1 - beta is formed in double before rounding to fp32).  lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) is
+ * computed by the caller.  param / m / v are updated in place; all pointers 16-byte aligned.  NaN gradients count
+ * as zero; an element whose step would cross a bound moves half-way to it and has its moments reset. */
+VP_API int vp_bounded_adam_step(int64_t n, float *param, const float *grad, float *m, float *v, double lr_t, double beta1,
+                                double beta2, double eps, int has_lower, float lower, int has_upper, float upper,
+                                void *stream);
+
 /* Introspection for tests: copies the BVH node array (16 floats per internal node, layout in
  * csrc/vp_build.cu) and the sorted->original index into caller device buffers (either may be NULL);
  * *n_internal receives the internal-node count (N-1). */

@@ -81,6 +81,8 @@ class BoundedAdam:
             lr_t = self.lr.get(k, self.lr_default) * lr_scale
             if p.grad is None:
                 continue
+            if self._fused_step(k, p, lr_t, has_mask):
+                continue
             g_p = torch.nan_to_num(p.grad, nan=0.0, posinf=float('inf'), neginf=float('-inf'))  # isnan -> 0 (:88)
             m_tp, v_tp = self.state[k]
             m_t = self.beta_1 * m_tp + (1 - self.beta_1) * g_p
@@ -114,6 +116,31 @@ class BoundedAdam:
                 v_t = torch.where(over, torch.zeros_like(v_t), v_t)
             self.state[k] = (m_t, v_t)
             self.variables[k] = u.detach().requires_grad_(True)
+
+    def _fused_step(self, k, p, lr_t, has_mask) -> bool:
+        """One fused CUDA pass (csrc/vp_optim.cu) for the plain variant on CUDA tensors; the masked / uniform variants
+        and CPU tensors use the torch ops below (same arithmetic)."""
+        if not p.is_cuda or self.mask_updates or self.uniform or has_mask or p.dtype != torch.float32:
+            return False
+        import ctypes as C
+        from . import _cabi
+        lib = _cabi.load_library()
+        val = p.detach().contiguous().clone()
+        g = p.grad.detach().contiguous()
+        m, v = self.state[k]
+        m, v = m.contiguous(), v.contiguous()
+        upper, lower = self.bounds.get(k, (None, None))
+        ptr = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(p.device):
+            rc = lib.vp_bounded_adam_step(val.numel(), ptr(val), ptr(g), ptr(m), ptr(v), float(lr_t), self.beta_1,
+                                          self.beta_2, self.epsilon, int(lower is not None), float(lower or 0.0),
+                                          int(upper is not None), float(upper or 0.0),
+                                          C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream))
+        if rc != 0:
+            raise _cabi.VolprimCudaError(f"vp_bounded_adam_step failed ({rc})")
+        self.state[k] = (m, v)
+        self.variables[k] = val.requires_grad_(True)
+        return True
 
     def __repr__(self):
         return ('BoundedAdam[\n  variables = %s,\n  lr = %s,\n  betas = (%g, %g),\n  eps = %g\n  bounds = %s\n]'
