@@ -180,16 +180,32 @@ __device__ __forceinline__ void list_insert(int *s_id, float *s_t, int n, float 
     s_id[j * STRIDE] = pos;
 }
 
-template <int STRIDE, class OnHit>
-__device__ __forceinline__ void drain_list(const DevScene &S, const int *s_id, float *s_t, int n_found, const float3 &o,
+// same for the tile walker's lists: one 64-bit key (distance bits << 32 | position) per entry, so an insertion moves
+// one shared-memory word pair instead of two separate arrays (positive floats order like their bit patterns)
+template <int STRIDE>
+__device__ __forceinline__ void list_insert_key(unsigned long long *s_key, int n, float tn, int pos)
+{
+    const unsigned long long key = ((unsigned long long)(tn > 0.f ? __float_as_uint(tn) : 0u) << 32) | (unsigned)pos;
+    int j = n;
+    while (j > 0) {
+        const unsigned long long kp = s_key[(j - 1) * STRIDE];
+        if (!(kp > key)) break;
+        s_key[j * STRIDE] = kp;
+        --j;
+    }
+    s_key[j * STRIDE] = key;
+}
+
+template <class GetPos, class OnHit>
+__device__ __forceinline__ void drain_list(const DevScene &S, int n_found, GetPos &&get_pos, const float3 &o,
                                            const float3 d, float maxt, bool &alive, bool &missed, OnHit &&on_hit)
 {
     VP_CHECK(n_found >= 0 && n_found <= 64, 5, n_found, 0);
-    if (alive && n_found > 0) prefetch_prim(S, s_id[0]);
+    if (alive && n_found > 0) prefetch_prim(S, get_pos(0));
     for (int k = 0; alive && k < n_found; ++k) {
-        const int pos = s_id[k * STRIDE];
+        const int pos = get_pos(k);
         VP_CHECK(pos >= 0 && pos < S.n, 6, pos, k);
-        if (k + 1 < n_found) prefetch_prim(S, s_id[(k + 1) * STRIDE]);
+        if (k + 1 < n_found) prefetch_prim(S, get_pos(k + 1));
         float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
         Mat3 Rm = vp_quat_to_matrix_rn(g2);
         Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
@@ -334,7 +350,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
         __syncwarp();
         // ---- phase 3: drain in increasing distance ----
         const int n_found = n_h;
-        drain_list<TRACE_THREADS>(S, s_id, s_t, n_found, o, d, maxt, alive, missed, on_hit);
+        drain_list(S, n_found, [&](int k) { return s_id[k * TRACE_THREADS]; }, o, d, maxt, alive, missed, on_hit);
         // ---- next interval ----
         if (alive) {
             if (S.root < 0) { missed = true; alive = false; }
@@ -428,7 +444,8 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
     // shared memory: [hit ids CAP x 128][hit t CAP x 128][per warp: node queue, tile candidates].  The per-ray
     // fallback runs per WARP while the other warps of the block keep walking, so it re-uses exactly this warp's
     // list columns (a wider layout would overwrite the neighbours' queues -- found the hard way)
-    int *s_id = smem + threadIdx.x;
+    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(smem) + threadIdx.x;
+    int *s_id = smem + threadIdx.x;                                       // int / float views for the per-ray fallback
     float *s_t = reinterpret_cast<float *>(smem) + TILE_HIT_CAP * TRACE_THREADS + threadIdx.x;
     int *w_queue = smem + 2 * TILE_HIT_CAP * TRACE_THREADS + (threadIdx.x >> 5) * (TILE_QCAP + TILE_CCAP);
     int *w_cand = w_queue + TILE_QCAP;
@@ -565,7 +582,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
                 for (int u = 0; u < 4; ++u) {
                     if (alive && k0 + u < tcn && ok[u] && tn[u] > t_lo && tn[u] <= t_end) {
                         if (n_h < TILE_HIT_CAP) {
-                            list_insert<TRACE_THREADS>(s_id, s_t, n_h, tn[u], pos[u]);
+                            list_insert_key<TRACE_THREADS>(s_key, n_h, tn[u], pos[u]);
                             ++n_h;
                         } else lane_ovf = true;
                     }
@@ -587,7 +604,8 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         // ---- phase 3: drain (per lane) ----
         int found_sum = n_h;
         for (int off = 16; off; off >>= 1) found_sum += __shfl_xor_sync(FULL, found_sum, off);
-        drain_list<TRACE_THREADS>(S, s_id, s_t, n_h, o, d, maxt, alive, missed, on_hit);
+        drain_list(S, n_h, [&](int k) { return (int)(unsigned)(s_key[k * TRACE_THREADS] & 0xffffffffull); }, o, d, maxt, alive,
+                   missed, on_hit);
         // ---- next interval (warp-uniform) ----
         t_start = t_end;
         const float avg = (float)found_sum * inv_n;
