@@ -190,3 +190,26 @@ def test_tile_walker_fallback_does_not_disturb_neighbour_warps():
     assert float(same.float().mean()) > 0.995
     ref = oracle_scene(cloud).forward(op, o, d, mt, cap=128, fragility=True)
     print(compare_forward(a, ref, 128))
+
+
+def test_mixed_block_some_warps_hand_over_to_per_ray_walker():
+    """A nested cluster in the image centre inside an ordinary cloud: within one thread block some warps overflow
+    their lists and continue with the per-ray walker while their neighbours keep walking cooperatively (regression:
+    the hand-over must only touch the thread's own shared-memory slots)."""
+    rng = np.random.default_rng(11)
+    base = _cloud(n=20000, seed=6, crossings=30)
+    m = 300
+    nest = synthetic.make_cloud(m, 0.05, seed=7, sh_degree=3)
+    nest.data[:, 0:3] = rng.normal(0, 0.003, size=(m, 3))
+    nest.data[:, 3:6] = (0.02 + 0.06 * rng.random((m, 1))) * (1 + 0.2 * rng.random((m, 3)))
+    nest.opacities[:] = 0.02
+    cloud = synthetic.Cloud(np.concatenate([base.data, nest.data]), np.concatenate([base.opacities, nest.opacities]),
+                            np.concatenate([base.sh_coeffs, nest.sh_coeffs]), 3.0)
+    o, d, mt = _rays(view=2, w=128, h=64)
+    acc = gpu_scene(cloud)
+    p, op = make_params(0, 0, max_depth=-1, image=(128, 64))
+    res = acc.trace_forward(p, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt), record_cap=400)
+    ref = oracle_scene(cloud).forward(op, o, d, mt, cap=400, fragility=True)
+    st = compare_forward(res, ref, 400, max_fragile_frac=0.02)
+    assert ref.nhits.max() > 150 and np.median(ref.nhits) < 60      # only the centre tiles are dense
+    print(st)

@@ -30,10 +30,10 @@
 namespace {
 
 #ifndef VP_CAND_CAP
-#define VP_CAND_CAP 38   // 5 blocks x 38 KB of shared memory per SM
+#define VP_CAND_CAP 36   // 6 blocks x 36 KB of shared memory per SM
 #endif
 #ifndef VP_MIN_BLOCKS
-#define VP_MIN_BLOCKS 5   // 96 registers / thread; measured best on cfg2 (4: -9%, 6: -1%, 8: -25%)
+#define VP_MIN_BLOCKS 6   // 80 registers / thread; measured on cfg2: 4 blocks +13 %, 5: +4 %, 7: +8 %, 8: +25 % time
 #endif
 constexpr int CAND_CAP = VP_CAND_CAP;     // candidate / hit list entries per ray (shared memory: 8 B each)
 #ifndef VP_TARGET_HITS
@@ -46,9 +46,9 @@ constexpr int NODE_SENTINEL = 0x7fffffff;
 constexpr size_t TRACE_SMEM = (size_t)CAND_CAP * TRACE_THREADS * 8;
 // warp-cooperative (tile) walker: per-lane hit lists + per-warp node queue and tile candidate list
 #ifndef VP_TILE_HIT_CAP
-#define VP_TILE_HIT_CAP 28
+#define VP_TILE_HIT_CAP 24
 #define VP_TILE_QCAP 512
-#define VP_TILE_CCAP 320
+#define VP_TILE_CCAP 256
 #endif
 constexpr int TILE_HIT_CAP = VP_TILE_HIT_CAP;
 constexpr int TILE_QCAP = VP_TILE_QCAP;
@@ -219,7 +219,7 @@ __device__ __forceinline__ void drain_list(const DevScene &S, int n_found, GetPo
 // reference's order.  on_hit evaluates the primitive, advances the origin `o` (captured by the caller) and
 // returns false to terminate the ray.  WARP-CONVERGENT: all 32 lanes call it (lanes without a ray pass
 // alive = false).  s_id / s_t are this thread's columns of the shared candidate list (stride TRACE_THREADS).
-template <int CAP = CAND_CAP, class OnHit>
+template <int CAP = CAND_CAP, int STRIDE = TRACE_THREADS, class OnHit>
 __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_t, const float3 &o, const float3 o0,
                                          const float3 d, const float maxt, bool alive, bool &missed, Counters &cn,
                                          OnHit &&on_hit, const float t_begin = 0.f)
@@ -278,11 +278,11 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
             if (right >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.nodes + 4ll * right));
 #endif
             if (hl && left < 0) {
-                if (n_c < CAP) s_id[n_c * TRACE_THREADS] = ~left;
+                if (n_c < CAP) s_id[n_c * STRIDE] = ~left;
                 ++n_c;
             }
             if (hr && right < 0) {
-                if (n_c < CAP) s_id[n_c * TRACE_THREADS] = ~right;
+                if (n_c < CAP) s_id[n_c * STRIDE] = ~right;
                 ++n_c;
             }
             const bool vl = hl && left >= 0, vr = hr && right >= 0;
@@ -335,13 +335,13 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
             if (best_pos >= 0) { s_id[0] = best_pos; s_t[0] = best_t; n_h = 1; }
         } else if (!overflow) {
             for (int k = 0; k < n_c; ++k) {
-                const int pos = s_id[k * TRACE_THREADS];
+                const int pos = s_id[k * STRIDE];
                 float tn;
                 bool ok;
                 if (S.root >= 0) ok = fast_isect(S, pos, o0, d, tn);
                 else { ok = true; tn = 1.f; }
                 if (ok && tn > t_lo && tn <= t_end) {
-                    list_insert<TRACE_THREADS>(s_id, s_t, n_h, tn, pos);   // n_h <= k: entry k is already read
+                    list_insert<STRIDE>(s_id, s_t, n_h, tn, pos);   // n_h <= k: entry k is already read
                     ++n_h;
                 }
             }
@@ -350,7 +350,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
         __syncwarp();
         // ---- phase 3: drain in increasing distance ----
         const int n_found = n_h;
-        drain_list(S, n_found, [&](int k) { return s_id[k * TRACE_THREADS]; }, o, d, maxt, alive, missed, on_hit);
+        drain_list(S, n_found, [&](int k) { return s_id[k * STRIDE]; }, o, d, maxt, alive, missed, on_hit);
         // ---- next interval ----
         if (alive) {
             if (S.root < 0) { missed = true; alive = false; }
@@ -445,8 +445,10 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
     // fallback runs per WARP while the other warps of the block keep walking, so it re-uses exactly this warp's
     // list columns (a wider layout would overwrite the neighbours' queues -- found the hard way)
     unsigned long long *s_key = reinterpret_cast<unsigned long long *>(smem) + threadIdx.x;
-    int *s_id = smem + threadIdx.x;                                       // int / float views for the per-ray fallback
-    float *s_t = reinterpret_cast<float *>(smem) + TILE_HIT_CAP * TRACE_THREADS + threadIdx.x;
+    // the per-ray fallback keeps (id, t) in the two halves of THIS thread's 64-bit slots (row stride 256 words), so
+    // that it never touches a slot of another thread -- the other warps of the block keep using theirs
+    int *s_id = smem + 2 * threadIdx.x;
+    float *s_t = reinterpret_cast<float *>(smem) + 2 * threadIdx.x + 1;
     int *w_queue = smem + 2 * TILE_HIT_CAP * TRACE_THREADS + (threadIdx.x >> 5) * (TILE_QCAP + TILE_CCAP);
     int *w_cand = w_queue + TILE_QCAP;
     int *fb_id = s_id;
@@ -455,7 +457,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
     missed = false;
     if (S.n <= 0) { missed = alive; return; }
     if (S.root < 0) {   // single primitive: nothing to share
-        walk_ray<TILE_FALLBACK_CAP>(S, fb_id, fb_t, o, o0, d, maxt, alive, missed, cn, on_hit);
+        walk_ray<TILE_FALLBACK_CAP, 2 * TRACE_THREADS>(S, fb_id, fb_t, o, o0, d, maxt, alive, missed, cn, on_hit);
         return;
     }
     const float delta0 = __ldg(S.info + 6);
@@ -496,7 +498,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
             const Capsule c0 = tile_capsule(alive, am0, o0, d, t_start, t_start + delta0);
             if (c0.r > 2.f * __ldg(S.info + 8)) {
                 bool m2 = false;   // lanes that missed the scene box keep their `missed`
-                walk_ray<TILE_FALLBACK_CAP>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit);
+                walk_ray<TILE_FALLBACK_CAP, 2 * TRACE_THREADS>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit);
                 missed = missed || m2;
                 return;
             }
@@ -595,7 +597,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
             if (delta < delta_min) {   // cannot be listed: the per-ray walker has the closest-hit fallback
                 bool m2 = false;
                 __syncwarp();
-                walk_ray<TILE_FALLBACK_CAP>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit, t_start);
+                walk_ray<TILE_FALLBACK_CAP, 2 * TRACE_THREADS>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit, t_start);
                 missed = missed || m2;
                 return;
             }
@@ -834,10 +836,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
     float beta = 1.f, L[3] = { 0.f, 0.f, 0.f };
     uint32_t depth = 0;
     bool missed = false;
-    constexpr int NY = (D >= 0) ? (D + 1) * (D + 1) : 1;
-    float Y[NY];
-    if constexpr (INTEG == VP_INTEGRATOR_RF && D >= 0) sh_basis<(D >= 0 ? D : 0)>(d, Y);
-    else Y[0] = 0.f;
 
     auto on_hit = [&](int pos, float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is) -> bool {
         float T;
@@ -845,7 +843,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
             RfEval e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
             T = e.T;
             float raw[3] = { 0.f, 0.f, 0.f };
-            if constexpr (D >= 0) sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw);
+            if constexpr (D >= 0) {
+                // the SH basis is re-evaluated per hit (~35 instructions) instead of holding 16 registers across the
+                // whole walk: lower register pressure buys a sixth resident block per SM
+                float Y[(D >= 0) ? (D + 1) * (D + 1) : 1];
+                sh_basis<(D >= 0 ? D : 0)>(d, Y);
+                sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw);
+            }
             const float omt = 1.f - T;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
