@@ -193,3 +193,65 @@ def test_fused_bounded_adam_matches_torch_reference_rule():
             assert int(bad.sum()) <= 20, f"{int(bad.sum())} elements differ"
     x = a["x"].detach()
     assert float(x.min()) >= 1e-6 and float(x.max()) <= 0.25 and bool(((a.state["x"][0] == 0).sum() > 0))
+
+
+def test_batch_sensor_tent_filter_and_tomography_autograd():
+    """Batch sensor (views side by side, refine_3dg_dataset.py:96-107) with jittered samples + tent filter, and the
+    tomography plugin through render() / autograd against the oracle adjoint on pixel-centre rays."""
+    n = 2000
+    cloud = synthetic.make_cloud(n, synthetic.sigma0_for_hits(n, 15), seed=31, sh_degree=0)
+    sig = np.random.default_rng(1).uniform(0.0005, 0.01, n).astype(np.float32)
+    cams = [synthetic.ring_camera(i, 8, 40, 24) for i in (0, 3, 5)]
+    sd = {"type": "scene", "integrator": {"type": "volprim_tomography", "max_depth": -1},
+          "primitives": {"type": "ellipsoidsmesh", "centers": cloud.data[:, :3], "scales": cloud.data[:, 3:6],
+                         "quaternions": cloud.data[:, 6:], "sigma_t": sig[:, None], "albedo": np.ones((n, 3), np.float32),
+                         "extent": 3.0},
+          "environment": {"type": "constant", "radiance": 0.8}}
+    scene = vp.load_dict(sd)
+    batch = vp.load_dict({"type": "batch", "film": {"type": "hdrfilm", "width": 120, "height": 24, "filter": {"type": "tent"}},
+                          **{f"cam_{i}": _sensor_dict(c, "tent") for i, c in enumerate(cams)}})
+    img = vp.render(scene, sensor=batch, spp=4, seed=3)
+    assert img.shape == (24, 120, 3) and bool(torch.isfinite(img).all())
+    singles = [vp.render(scene, sensor=vp.load_dict(_sensor_dict(c, "box")), spp=1, jitter=False) for c in cams]
+    ref_strip = vp.utils.concatenate_tensors(singles)
+    # a jittered, tent-filtered estimate of the same (high-frequency, coarse) picture: compare the view means
+    for v in range(3):
+        a, b = img[:, 40 * v:40 * (v + 1)].mean(), ref_strip[:, 40 * v:40 * (v + 1)].mean()
+        assert abs(float(a - b)) < 0.03
+    # autograd through the tomography adjoint
+    params = vp.traverse(scene)
+    for k in ("primitives.data", "primitives.sigma_t"):
+        params[k].requires_grad_(True)
+    s0 = vp.load_dict(_sensor_dict(cams[1], "box"))
+    im = vp.render(scene, params, sensor=s0, spp=1, jitter=False)
+    w = torch.from_numpy(np.random.default_rng(5).normal(size=(24, 40, 3)).astype(np.float32)).cuda()
+    (im * w).sum().backward()
+    o, d, mt = synthetic.camera_rays(cams[1])
+    osc = O.Scene(cloud.data, sig, None, 3.0)
+    op = O.Params(integrator=O.TOMO, kernel=O.GAUSS, max_depth=-1, env=(0.8, 0.8, 0.8))
+    ref = osc.forward(op, o, d, mt)
+    np.testing.assert_allclose(im.detach().reshape(-1, 3).cpu().numpy(), ref.rgb, atol=2e-4, rtol=2e-3)
+    rd, ra, _ = osc.adjoint(op, o, d, w.reshape(-1, 3).cpu().numpy(), ref.rgb, mt)
+    grad_close(params["primitives.data"].grad.cpu().numpy(), rd, rtol=5e-3, what="tomography d data")
+    grad_close(params["primitives.sigma_t"].grad.cpu().numpy(), ra, rtol=5e-3, what="tomography d sigma_t")
+
+
+def test_explicit_ray_batches_nonunit_directions_and_finite_maxt():
+    """The radiance-cache calling convention (scripts/radiosity/radiance_cache.py:252-266): arbitrary rays, not from a
+    sensor -- random origins on a sphere, un-normalised directions, finite maxt that ends some rays inside the cloud."""
+    n = 30000
+    cloud = synthetic.make_cloud(n, synthetic.sigma0_for_hits(n, 40), seed=41, sh_degree=3)
+    rng = np.random.default_rng(9)
+    R = 4096
+    o = rng.normal(size=(R, 3))
+    o = (2.5 * o / np.linalg.norm(o, axis=1, keepdims=True)).astype(np.float32)
+    tgt = rng.uniform(-0.8, 0.8, size=(R, 3))
+    d = ((tgt - o) * rng.uniform(0.5, 2.0, size=(R, 1))).astype(np.float32)        # |d| != 1
+    mt = rng.uniform(0.3, 2.0, size=R).astype(np.float32)                          # in units of |d|
+    p, op = make_params(0, 0, max_depth=64)
+    acc = gpu_scene(cloud)
+    res = acc.trace_forward(p, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt), record_cap=64)
+    ref = oracle_scene(cloud).forward(op, o, d, mt, cap=64, fragility=True)
+    st = compare_forward(res, ref, 64)
+    assert 2 < st["mean_hits"] < 40
+    print(st)
