@@ -45,9 +45,16 @@ constexpr int TRACE_THREADS = 128;
 constexpr int NODE_SENTINEL = 0x7fffffff;
 constexpr size_t TRACE_SMEM = (size_t)CAND_CAP * TRACE_THREADS * 8;
 // warp-cooperative (tile) walker: per-lane hit lists + per-warp node queue and tile candidate list
+#ifndef VP_FILL
+#define VP_FILL 0.55f
+#endif
 #ifndef VP_TILE_HIT_CAP
 #define VP_TILE_HIT_CAP 24
+#endif
+#ifndef VP_TILE_QCAP
 #define VP_TILE_QCAP 512
+#endif
+#ifndef VP_TILE_CCAP
 #define VP_TILE_CCAP 256
 #endif
 constexpr int TILE_HIT_CAP = VP_TILE_HIT_CAP;
@@ -456,10 +463,11 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
     const unsigned lt = (1u << lane) - 1u;
     missed = false;
     if (S.n <= 0) { missed = alive; return; }
-    if (S.root < 0) {   // single primitive: nothing to share
-        walk_ray<TILE_FALLBACK_CAP, 2 * TRACE_THREADS>(S, fb_id, fb_t, o, o0, d, maxt, alive, missed, cn, on_hit);
-        return;
-    }
+    // The per-ray walker takes over (from distance t_hand) when the tile walk returns true; it is instantiated at this
+    // one place only -- the kernel is issue-bound and every inlined copy costs registers and instruction cache.
+    float t_hand = 0.f;
+    auto tile_part = [&]() -> bool {
+    if (S.root < 0) return true;   // single primitive: nothing to share
     const float delta0 = __ldg(S.info + 6);
     const float delta_min = delta0 * (1.f / 4096.f);
     float t_in = VP_INF, t_out = -VP_INF;
@@ -488,7 +496,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
     int rs_node = lane == 0 ? S.root : -1, rs_n = 1;
     {
         const unsigned am0 = __ballot_sync(FULL, alive);
-        if (!am0) return;
+        if (!am0) return false;
         float t_far = alive ? t_out : -VP_INF;
         for (int off = 16; off; off >>= 1) t_far = fmaxf(t_far, __shfl_xor_sync(FULL, t_far, off));
         // A tile much wider than the primitives (coarse images, incoherent "tiles") would list several times more
@@ -497,10 +505,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         {
             const Capsule c0 = tile_capsule(alive, am0, o0, d, t_start, t_start + delta0);
             if (c0.r > 2.f * __ldg(S.info + 8)) {
-                bool m2 = false;   // lanes that missed the scene box keep their `missed`
-                walk_ray<TILE_FALLBACK_CAP, 2 * TRACE_THREADS>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit);
-                missed = missed || m2;
-                return;
+                return true;
             }
         }
         const Capsule cf = tile_capsule(alive, am0, o0, d, fmaxf(t_start - 1e-3f, 0.f), t_far);
@@ -528,7 +533,6 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
     while (true) {
         const unsigned am = __ballot_sync(FULL, alive);
         if (!am) break;
-        const float inv_n = 1.f / (float)__popc(am);
         const float t_lo = t_start - (1e-4f + 1e-5f * t_start);
         const float t_end = t_start + delta;
         if (alive) cn.passes++;
@@ -539,6 +543,8 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         if (lane < rs_n) w_queue[lane] = rs_node;
         __syncwarp();
         while (qn > 0) {
+            // every popped node pushes at most two children: taking no more than half of the free space per step
+            // means the queue cannot overflow (a nearly full queue is drained depth-first in small bites)
             const int take = qn < 32 ? qn : 32;
             const int base = qn - take;
             const int node = lane < take ? w_queue[base + lane] : -1;
@@ -570,7 +576,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         // ---- phase 2: every lane tests the tile's candidates against its own ray ----
         // (warp-uniform loop, broadcast loads; four candidates per trip so that their loads overlap)
         int n_h = 0;
-        bool lane_ovf = false;
+        bool dropped = false;   // this lane saw more entries than its list holds and kept the closest ones
         if (!overflow) {
             for (int k0 = 0; k0 < tcn; k0 += 4) {
                 int pos[4];
@@ -582,37 +588,76 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
                 for (int u = 0; u < 4; ++u) ok[u] = fast_isect(S, pos[u], o0, d, tn[u]);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (alive && k0 + u < tcn && ok[u] && tn[u] > t_lo && tn[u] <= t_end) {
-                        if (n_h < TILE_HIT_CAP) {
-                            list_insert_key<TRACE_THREADS>(s_key, n_h, tn[u], pos[u]);
-                            ++n_h;
-                        } else lane_ovf = true;
+                    bool take = alive && k0 + u < tcn && ok[u] && tn[u] > t_lo && tn[u] <= t_end;
+                    if (take && n_h == TILE_HIT_CAP) {
+                        // full: the list keeps its TILE_HIT_CAP closest entries (the farthest one falls out)
+                        dropped = true;
+                        const unsigned last_t = (unsigned)(s_key[(TILE_HIT_CAP - 1) * TRACE_THREADS] >> 32);
+                        if (__float_as_uint(tn[u]) < last_t) n_h = TILE_HIT_CAP - 1;
+                        else take = false;
+                    }
+                    if (take) {
+                        list_insert_key<TRACE_THREADS>(s_key, n_h, tn[u], pos[u]);
+                        ++n_h;
                     }
                 }
             }
             if (alive) cn.candidates += tcn;
         }
-        if (overflow || __any_sync(FULL, lane_ovf)) {
+        if (overflow) {   // the tile's candidate list or the node queue did not fit: shorter interval, walk again
+            if (alive) cn.overflow++;   // (statistics: interval retries)
             delta *= 0.5f;
             if (delta < delta_min) {   // cannot be listed: the per-ray walker has the closest-hit fallback
-                bool m2 = false;
-                __syncwarp();
-                walk_ray<TILE_FALLBACK_CAP, 2 * TRACE_THREADS>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit, t_start);
-                missed = missed || m2;
-                return;
+                t_hand = t_start;
+                return true;
             }
             continue;
         }
+        // A lane that dropped entries is complete only up to its farthest kept entry.  Nothing is walked again: the
+        // WHOLE tile ends the interval there (the collected candidates cover it), every lane keeps its entries up to
+        // that distance, and the next interval starts from it.
+        float t_cut = dropped ? __uint_as_float((unsigned)(s_key[(TILE_HIT_CAP - 1) * TRACE_THREADS] >> 32)) : VP_INF;
+        for (int off = 16; off; off >>= 1) t_cut = fminf(t_cut, __shfl_xor_sync(FULL, t_cut, off));
+        float t_done = t_end;
+        if (t_cut < t_end && !(t_cut - t_start > delta_min)) {
+            // more entries than a list holds within the smallest interval (heavy overlap): no progress possible here,
+            // the per-ray walker's closest-hit search takes over from the current position
+            t_hand = t_start;
+            return true;
+        }
+        if (t_cut < t_end) {
+            t_done = t_cut;
+            const unsigned cut_bits = __float_as_uint(t_cut);
+            while (n_h > 0 && (unsigned)(s_key[(n_h - 1) * TRACE_THREADS] >> 32) > cut_bits) --n_h;
+        }
         // ---- phase 3: drain (per lane) ----
-        int found_sum = n_h;
-        for (int off = 16; off; off >>= 1) found_sum += __shfl_xor_sync(FULL, found_sum, off);
+        const int found_max = (int)__reduce_max_sync(FULL, (unsigned)n_h);
         drain_list(S, n_h, [&](int k) { return (int)(unsigned)(s_key[k * TRACE_THREADS] & 0xffffffffull); }, o, d, maxt, alive,
                    missed, on_hit);
         // ---- next interval (warp-uniform) ----
-        t_start = t_end;
-        const float avg = (float)found_sum * inv_n;
-        delta *= (avg < 0.25f * (float)TARGET_HITS) ? 4.f : fminf(fmaxf((float)TARGET_HITS / avg, 0.5f), 2.f);
+        // the interval grows or shrinks so that the fullest of the lists it has to fit -- the busiest lane's hit list
+        // and the tile's candidate list -- lands at VP_FILL of its capacity; after a cut it restarts from the width
+        // that actually fitted
+        if (t_done < t_end) delta = fmaxf((t_done - t_start) * 0.75f, delta_min);
+        else {
+            const float fill_h = (float)found_max * (1.f / (VP_FILL * TILE_HIT_CAP));
+            const float fill_c = (float)tcn * (1.f / (VP_FILL * TILE_CCAP));
+            const float f_h = (fill_h < 0.15f) ? 4.f : fminf(fmaxf(1.f / fill_h, 0.5f), 2.f);
+            // the candidate count only shrinks the interval while that can help: boxes that contain the whole
+            // neighbourhood (nested primitives) stay candidates however short the interval gets
+            const float f_c = fmaxf(1.f / fmaxf(fill_c, 0.25f), delta > delta0 * (1.f / 32.f) ? 0.5f : 1.f);
+            delta = fmaxf(delta * fminf(f_h, f_c), delta_min);
+        }
+        t_start = t_done;
         if (alive && t_start > t_out) { missed = true; alive = false; }
+    }
+    return false;
+    };
+    if (tile_part()) {
+        bool m2 = false;   // lanes that missed the scene box keep their `missed`
+        __syncwarp();
+        walk_ray<TILE_FALLBACK_CAP, 2 * TRACE_THREADS>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit, t_hand);
+        missed = missed || m2;
     }
 }
 
