@@ -63,25 +63,63 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (2 ms period; the timed
+    region of the default run lasts < 100 ms, too short for an `nvidia-smi -lms` child to start), with `nvidia-smi`
+    as the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.index, self.proc, self.path = index, None, None
+        self.rows, self.thread, self.stop, self.max_mhz, self.source = [], None, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # under torchrun every rank sees all GPUs: LOCAL_RANK is the NVML index unless CUDA_VISIBLE_DEVICES remaps
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        bits = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        while not self.stop:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((mhz, [n for n, b in bits if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
+        if self.nv is not None:
+            import threading
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi"
         except Exception:
             self.proc = None
         return self
 
     def __exit__(self, *exc):
+        if self.thread is not None:
+            self.stop = True
+            self.thread.join(timeout=2)
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
@@ -92,6 +130,13 @@ class ClockSampler:
 
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None and self.rows:
+            out["sm_mhz"] = statistics.median(r[0] for r in self.rows)
+            out["sm_max_mhz"] = self.max_mhz
+            out["reasons"] = sorted({n for r in self.rows for n in r[1]})
+            out["samples"] = len(self.rows)
+            out["source"] = self.source
+            return out
         try:
             rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
             sm = [float(r[0]) for r in rows]
@@ -102,11 +147,13 @@ class ClockSampler:
                 if any("Active" == r[2 + i].strip() for r in rows):
                     out["reasons"].append(nme)
             out["samples"] = len(rows)
+            out["source"] = self.source
         except Exception:
             pass
         finally:
             try:
-                os.unlink(self.path)
+                if self.path:
+                    os.unlink(self.path)
             except Exception:
                 pass
         return out

@@ -48,6 +48,18 @@ constexpr size_t TRACE_SMEM = (size_t)CAND_CAP * TRACE_THREADS * 8;
 #ifndef VP_FILL
 #define VP_FILL 0.55f
 #endif
+#ifndef VP_OVF_SHRINK
+#define VP_OVF_SHRINK 0.35f
+#endif
+#ifndef VP_GROW_MAX
+#define VP_GROW_MAX 2.f
+#endif
+#ifndef VP_CSHRINK_FLOOR
+#define VP_CSHRINK_FLOOR 32.f
+#endif
+#ifndef VP_CAND_TARGET
+#define VP_CAND_TARGET (VP_FILL * VP_TILE_CCAP)
+#endif
 #ifndef VP_TILE_HIT_CAP
 #define VP_TILE_HIT_CAP 24
 #endif
@@ -55,7 +67,7 @@ constexpr size_t TRACE_SMEM = (size_t)CAND_CAP * TRACE_THREADS * 8;
 #define VP_TILE_QCAP 512
 #endif
 #ifndef VP_TILE_CCAP
-#define VP_TILE_CCAP 256
+#define VP_TILE_CCAP 192
 #endif
 constexpr int TILE_HIT_CAP = VP_TILE_HIT_CAP;
 constexpr int TILE_QCAP = VP_TILE_QCAP;
@@ -417,6 +429,90 @@ __device__ __forceinline__ Capsule tile_capsule(bool alive, unsigned am, float3 
     return c;
 }
 
+// Tighter bound of the same ray segments for the per-candidate cull (phase 1.5 of the tile walker): the mean segment
+// A + lambda D plus a BOX of deviations in the tile's own frame (u along the tile's pixel rows, w along the mean
+// direction, v = w x u) -- an 8x4 pixel tile is twice as wide as it is high, the capsule's circle wastes half its area.
+struct TilePrism {
+    float3 A, D, u, v, w;
+    float ra, rb, rw;
+};
+__device__ __forceinline__ TilePrism tile_prism(bool alive, unsigned am, float3 o0, float3 d, float t0, float t1)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const float inv_n = 1.f / (float)__popc(am);
+    const float3 P0 = make_float3(fmaf(d.x, t0, o0.x), fmaf(d.y, t0, o0.y), fmaf(d.z, t0, o0.z));
+    const float3 P1 = make_float3(fmaf(d.x, t1, o0.x), fmaf(d.y, t1, o0.y), fmaf(d.z, t1, o0.z));
+    float3 A = alive ? P0 : make_float3(0.f, 0.f, 0.f), B = alive ? P1 : make_float3(0.f, 0.f, 0.f);
+    for (int off = 16; off; off >>= 1) {
+        A.x += __shfl_xor_sync(FULL, A.x, off); A.y += __shfl_xor_sync(FULL, A.y, off); A.z += __shfl_xor_sync(FULL, A.z, off);
+        B.x += __shfl_xor_sync(FULL, B.x, off); B.y += __shfl_xor_sync(FULL, B.y, off); B.z += __shfl_xor_sync(FULL, B.z, off);
+    }
+    A.x *= inv_n; A.y *= inv_n; A.z *= inv_n; B.x *= inv_n; B.y *= inv_n; B.z *= inv_n;
+    TilePrism p;
+    p.A = A;
+    p.D = make_float3(B.x - A.x, B.y - A.y, B.z - A.z);
+    const float dl = rsqrtf(fmaxf(p.D.x * p.D.x + p.D.y * p.D.y + p.D.z * p.D.z, 1e-30f));
+    p.w = make_float3(p.D.x * dl, p.D.y * dl, p.D.z * dl);
+    // u: the direction from the tile's first to its last pixel of a row (lanes 0 and 7), made orthogonal to w.  ANY
+    // orthonormal frame keeps the bound valid; this one makes it tight for image tiles.
+    float3 ur = make_float3(__shfl_sync(FULL, P1.x, 7) - __shfl_sync(FULL, P1.x, 0),
+                            __shfl_sync(FULL, P1.y, 7) - __shfl_sync(FULL, P1.y, 0),
+                            __shfl_sync(FULL, P1.z, 7) - __shfl_sync(FULL, P1.z, 0));
+    float uw = ur.x * p.w.x + ur.y * p.w.y + ur.z * p.w.z;
+    ur = make_float3(ur.x - uw * p.w.x, ur.y - uw * p.w.y, ur.z - uw * p.w.z);
+    float ul = ur.x * ur.x + ur.y * ur.y + ur.z * ur.z;
+    if (!(ul > 1e-20f)) {   // degenerate tile: any direction perpendicular to w
+        ur = fabsf(p.w.x) < 0.6f ? make_float3(0.f, -p.w.z, p.w.y) : make_float3(-p.w.z, 0.f, p.w.x);
+        ul = ur.x * ur.x + ur.y * ur.y + ur.z * ur.z;
+    }
+    const float uil = rsqrtf(ul);
+    p.u = make_float3(ur.x * uil, ur.y * uil, ur.z * uil);
+    p.v = make_float3(p.w.y * p.u.z - p.w.z * p.u.y, p.w.z * p.u.x - p.w.x * p.u.z, p.w.x * p.u.y - p.w.y * p.u.x);
+    float ra = 0.f, rb = 0.f, rw = 0.f;
+    if (alive) {
+        const float3 e0 = make_float3(P0.x - A.x, P0.y - A.y, P0.z - A.z), e1 = make_float3(P1.x - B.x, P1.y - B.y, P1.z - B.z);
+        ra = fmaxf(fabsf(e0.x * p.u.x + e0.y * p.u.y + e0.z * p.u.z), fabsf(e1.x * p.u.x + e1.y * p.u.y + e1.z * p.u.z));
+        rb = fmaxf(fabsf(e0.x * p.v.x + e0.y * p.v.y + e0.z * p.v.z), fabsf(e1.x * p.v.x + e1.y * p.v.y + e1.z * p.v.z));
+        rw = fmaxf(fabsf(e0.x * p.w.x + e0.y * p.w.y + e0.z * p.w.z), fabsf(e1.x * p.w.x + e1.y * p.w.y + e1.z * p.w.z));
+    }
+    for (int off = 16; off; off >>= 1) {
+        ra = fmaxf(ra, __shfl_xor_sync(FULL, ra, off));
+        rb = fmaxf(rb, __shfl_xor_sync(FULL, rb, off));
+        rw = fmaxf(rw, __shfl_xor_sync(FULL, rw, off));
+    }
+    const float slack = 1e-6f * (1.f + fabsf(A.x) + fabsf(A.y) + fabsf(A.z));
+    p.ra = ra * 1.001f + slack; p.rb = rb * 1.001f + slack; p.rw = rw * 1.001f + slack;
+    return p;
+}
+
+// Can ANY ray of the tile touch the primitive's bounding ellipsoid?  In the primitive's unit-sphere space (x' = M (x -
+// c), the record fast_isect uses) the mean line passes the origin at distance |P|, P = A' - (A'.D^)D^.  Along e = P/|P|
+// a point of the prism lies at e.x' = |P| + g.q with g = M^T e and q the deviation, |g.q| <= ra|g.u| + rb|g.v| + rw|g.w|.
+// If that cannot come down to 1 no ray of the tile reaches the ellipsoid.  Conservative: never rejects a real hit.
+__device__ __forceinline__ bool prism_may_hit(const DevScene &S, int pos, const TilePrism &p)
+{
+    const float4 *x = S.xf + 3ll * pos;
+    const float4 r0 = __ldg(x), r1 = __ldg(x + 1), r2 = __ldg(x + 2);
+    const float3 a = make_float3(p.A.x - r0.w, p.A.y - r1.w, p.A.z - r2.w);
+    const float3 Ap = make_float3(r0.x * a.x + r0.y * a.y + r0.z * a.z, r1.x * a.x + r1.y * a.y + r1.z * a.z,
+                                  r2.x * a.x + r2.y * a.y + r2.z * a.z);
+    const float3 Dp = make_float3(r0.x * p.D.x + r0.y * p.D.y + r0.z * p.D.z, r1.x * p.D.x + r1.y * p.D.y + r1.z * p.D.z,
+                                  r2.x * p.D.x + r2.y * p.D.y + r2.z * p.D.z);
+    const float dd = Dp.x * Dp.x + Dp.y * Dp.y + Dp.z * Dp.z;
+    if (!(dd > 1e-30f)) return true;
+    const float k = (Ap.x * Dp.x + Ap.y * Dp.y + Ap.z * Dp.z) / dd;
+    const float3 P = make_float3(Ap.x - k * Dp.x, Ap.y - k * Dp.y, Ap.z - k * Dp.z);
+    const float pl2 = P.x * P.x + P.y * P.y + P.z * P.z;
+    if (!(pl2 > 1.f)) return true;          // the mean line itself passes through the bounding ellipsoid
+    const float ipl = rsqrtf(pl2), pl = pl2 * ipl;
+    const float3 e = make_float3(P.x * ipl, P.y * ipl, P.z * ipl);
+    const float3 g = make_float3(r0.x * e.x + r1.x * e.y + r2.x * e.z, r0.y * e.x + r1.y * e.y + r2.y * e.z,
+                                 r0.z * e.x + r1.z * e.y + r2.z * e.z);
+    const float h = p.ra * fabsf(g.x * p.u.x + g.y * p.u.y + g.z * p.u.z) + p.rb * fabsf(g.x * p.v.x + g.y * p.v.y + g.z * p.v.z)
+                  + p.rw * fabsf(g.x * p.w.x + g.y * p.w.y + g.z * p.w.z);
+    return !(pl > 1.002f + 1.002f * h);
+}
+
 // child boxes of one node against a capsule
 __device__ __forceinline__ void capsule_children(const DevScene &S, int node, const Capsule &c, bool &hl, bool &hr,
                                                  int &left, int &right)
@@ -573,6 +669,25 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
             __syncwarp();
         }
         __syncwarp();
+#ifndef VP_NO_PRISM_CULL
+        // ---- phase 1.5: lane-parallel cull of the candidates no ray of the tile can touch (more than half of what
+        // the box-vs-capsule walk lists: rotated anisotropic ellipsoids fill little of their boxes).  One candidate
+        // per lane, compacted in place; costs ~3 issue slots per candidate, phase 2 costs ~50 per surviving one. ----
+        if (!overflow && tcn > 0) {
+            const TilePrism pr = tile_prism(alive, am, o0, d, t_lo, t_end);
+            int kept = 0;
+            for (int k0 = 0; k0 < tcn; k0 += 32) {
+                const int k = k0 + lane;
+                const int pos = k < tcn ? w_cand[k] : -1;
+                const bool keep = pos >= 0 && prism_may_hit(S, pos, pr);
+                const unsigned mk = __ballot_sync(FULL, keep);
+                if (keep) w_cand[kept + __popc(mk & lt)] = pos;   // kept <= k0: never ahead of the reads
+                kept += __popc(mk);
+                __syncwarp();
+            }
+            tcn = kept;
+        }
+#endif
         // ---- phase 2: every lane tests the tile's candidates against its own ray ----
         // (warp-uniform loop, broadcast loads; four candidates per trip so that their loads overlap)
         int n_h = 0;
@@ -606,7 +721,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         }
         if (overflow) {   // the tile's candidate list or the node queue did not fit: shorter interval, walk again
             if (alive) cn.overflow++;   // (statistics: interval retries)
-            delta *= 0.5f;
+            delta *= VP_OVF_SHRINK;
             if (delta < delta_min) {   // cannot be listed: the per-ray walker has the closest-hit fallback
                 t_hand = t_start;
                 return true;
@@ -641,11 +756,11 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         if (t_done < t_end) delta = fmaxf((t_done - t_start) * 0.75f, delta_min);
         else {
             const float fill_h = (float)found_max * (1.f / (VP_FILL * TILE_HIT_CAP));
-            const float fill_c = (float)tcn * (1.f / (VP_FILL * TILE_CCAP));
-            const float f_h = (fill_h < 0.15f) ? 4.f : fminf(fmaxf(1.f / fill_h, 0.5f), 2.f);
+            const float fill_c = (float)tcn * (1.f / (float)(VP_CAND_TARGET));
+            const float f_h = (fill_h < 0.15f) ? VP_GROW_MAX : fminf(fmaxf(1.f / fill_h, 0.5f), 2.f);
             // the candidate count only shrinks the interval while that can help: boxes that contain the whole
             // neighbourhood (nested primitives) stay candidates however short the interval gets
-            const float f_c = fmaxf(1.f / fmaxf(fill_c, 0.25f), delta > delta0 * (1.f / 32.f) ? 0.5f : 1.f);
+            const float f_c = fmaxf(1.f / fmaxf(fill_c, 0.25f), delta > delta0 * (1.f / VP_CSHRINK_FLOOR) ? 0.5f : 1.f);
             delta = fmaxf(delta * fminf(f_h, f_c), delta_min);
         }
         t_start = t_done;
@@ -653,7 +768,12 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
     }
     return false;
     };
+#ifdef VP_EXP_NO_FALLBACK
+    tile_part();
+    if (false) {
+#else
     if (tile_part()) {
+#endif
         bool m2 = false;   // lanes that missed the scene box keep their `missed`
         __syncwarp();
         walk_ray<TILE_FALLBACK_CAP, 2 * TRACE_THREADS>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit, t_hand);
