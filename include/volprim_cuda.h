@@ -72,8 +72,10 @@ typedef struct vp_stats {
     uint64_t hits;        /* primitive evaluations (accepted hits)             */
     uint64_t candidates;  /* exact ray/ellipsoid tests during traversal        */
     uint64_t node_visits; /* BVH internal nodes fetched                        */
-    uint64_t passes;      /* k-buffer (re)fill passes                          */
-    uint64_t stack_overflows;
+    uint64_t passes;      /* intervals walked (hit-list refills), summed over rays */
+    uint64_t stack_overflows;  /* traversal-stack overflows of the per-ray walker: must be 0, a subtree was skipped */
+    uint64_t interval_retries; /* intervals walked again with a shorter width because a list did not fit (per ray;
+                                  performance statistic only) */
 } vp_stats;
 
 VP_API int vp_version(void);

@@ -4,7 +4,7 @@ rep = sys.argv[1]
 src = open('/root/repo/volprim_balance_b200/csrc/vp_trace.cu').read().split('\n')
 marks = []
 for i, l in enumerate(src, 1):
-    m = re.match(r'^(?:__device__ __forceinline__|__global__|template <.*>\s*$)?.*?\b(exact_isect|fast_isect|slab|drain_list|walk_ray|walk_tile|sh_basis|sh_color|rf_eval|gauss_density_integral|epan_density_integral|srgb_to_linear|ray_index|flush_counters|k_trace_forward|rf_adjoint_hit|tomo_adjoint_hit|k_trace_adjoint|k_raygen)\(', l)
+    m = re.match(r'^(?:__device__ __forceinline__|__global__|template <.*>\s*$)?.*?\b(exact_isect|fast_isect|slab|list_insert_key|list_insert|drain_list|walk_ray|tile_capsule|tile_prism|prism_may_hit|capsule_children|walk_tile|sh_basis|sh_color|rf_eval|gauss_density_integral|epan_density_integral|srgb_to_linear|ray_index|flush_counters|k_trace_forward|rf_adjoint_hit|tomo_adjoint_hit|k_trace_adjoint|k_raygen)\(', l)
     if m and (l.startswith('__device__') or l.startswith('__global__')): marks.append((i, m.group(1)))
 def fn(line):
     name = 'header'

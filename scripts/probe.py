@@ -28,7 +28,7 @@ for view in range(3):
         st = acc.stats()
         print(json.dumps({"view": view, "record": rec, "ms": ms, "mrays_s": W * H / ms / 1e3, "mean_hits": st["hits"] / (W * H),
                           "cand_per_ray": st["candidates"] / (W * H), "nodes_per_ray": st["node_visits"] / (W * H),
-                          "passes_per_ray": st["passes"] / (W * H), "overflow": st["stack_overflows"],
+                          "passes_per_ray": st["passes"] / (W * H), "overflow": st["stack_overflows"], "retries": st["interval_retries"],
                           "beta_mean": float(res.beta.mean())}))
     if view == 0:
         dL = torch.randn(W * H, 3, device="cuda")

@@ -25,4 +25,4 @@ for view in (0, 1):
         ms = min(ms, e0.elapsed_time(e1))
     st = acc.stats(); R = W * H
     print(json.dumps({"workload": name, "view": view, "ms": round(ms, 3), "hits": round(st["hits"] / R, 2), "cands": round(st["candidates"] / R, 1),
-                      "nodes": round(st["node_visits"] / R, 1), "passes": round(st["passes"] / R, 2), "overflow": st["stack_overflows"]}))
+                      "nodes": round(st["node_visits"] / R, 1), "passes": round(st["passes"] / R, 2), "overflow": st["stack_overflows"], "retries": st["interval_retries"]}))

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert lib.vp_version() == 100
     # struct layouts must match the header (sizes are part of the ABI)
     assert ctypes.sizeof(_cabi.vp_params) == 48 and ctypes.sizeof(_cabi.vp_camera) == 76
-    assert ctypes.sizeof(_cabi.vp_stats) == 48
+    assert ctypes.sizeof(_cabi.vp_stats) == 56
 
 
 def test_no_cpu_fallback_without_gpu():

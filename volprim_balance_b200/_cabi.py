@@ -58,6 +58,7 @@ class vp_stats(C.Structure):
         ("node_visits", C.c_uint64),
         ("passes", C.c_uint64),
         ("stack_overflows", C.c_uint64),
+        ("interval_retries", C.c_uint64),
     ]
 
 

@@ -46,7 +46,7 @@ constexpr int NODE_SENTINEL = 0x7fffffff;
 constexpr size_t TRACE_SMEM = (size_t)CAND_CAP * TRACE_THREADS * 8;
 // warp-cooperative (tile) walker: per-lane hit lists + per-warp node queue and tile candidate list
 #ifndef VP_FILL
-#define VP_FILL 0.55f
+#define VP_FILL 0.7f
 #endif
 #ifndef VP_OVF_SHRINK
 #define VP_OVF_SHRINK 0.35f
@@ -121,7 +121,7 @@ __device__ __forceinline__ Isect exact_isect(float3 o, float3 d, float4 g0, floa
 }
 
 struct Counters {
-    uint32_t hits, candidates, nodes, passes, overflow;
+    uint32_t hits, candidates, nodes, passes, overflow, retries;
 };
 
 // Approximate entry distance from the pre-transformed record xf (rows of M = diag(1/(extent s)) R^T with the
@@ -639,8 +639,6 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         if (lane < rs_n) w_queue[lane] = rs_node;
         __syncwarp();
         while (qn > 0) {
-            // every popped node pushes at most two children: taking no more than half of the free space per step
-            // means the queue cannot overflow (a nearly full queue is drained depth-first in small bites)
             const int take = qn < 32 ? qn : 32;
             const int base = qn - take;
             const int node = lane < take ? w_queue[base + lane] : -1;
@@ -720,7 +718,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
             if (alive) cn.candidates += tcn;
         }
         if (overflow) {   // the tile's candidate list or the node queue did not fit: shorter interval, walk again
-            if (alive) cn.overflow++;   // (statistics: interval retries)
+            if (alive) cn.retries++;   // (statistics)
             delta *= VP_OVF_SHRINK;
             if (delta < delta_min) {   // cannot be listed: the per-ray walker has the closest-hit fallback
                 t_hand = t_start;
@@ -950,9 +948,9 @@ __device__ __forceinline__ int64_t ray_index(int64_t t, int W, int H)
 __device__ __forceinline__ void flush_counters(const Counters &cn, vp_stats *st)
 {
     if (!st) return;
-    uint32_t v[5] = { cn.hits, cn.candidates, cn.nodes, cn.passes, cn.overflow };
+    uint32_t v[6] = { cn.hits, cn.candidates, cn.nodes, cn.passes, cn.overflow, cn.retries };
 #pragma unroll
-    for (int k = 0; k < 5; ++k)
+    for (int k = 0; k < 6; ++k)
         for (int off = 16; off; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
     if ((threadIdx.x & 31) == 0) {
         atomicAdd((unsigned long long *)&st->hits, (unsigned long long)v[0]);
@@ -960,6 +958,7 @@ __device__ __forceinline__ void flush_counters(const Counters &cn, vp_stats *st)
         atomicAdd((unsigned long long *)&st->node_visits, (unsigned long long)v[2]);
         atomicAdd((unsigned long long *)&st->passes, (unsigned long long)v[3]);
         if (v[4]) atomicAdd((unsigned long long *)&st->stack_overflows, (unsigned long long)v[4]);
+        if (v[5]) atomicAdd((unsigned long long *)&st->interval_retries, (unsigned long long)v[5]);
     }
 }
 
@@ -987,7 +986,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
     int *s_id = reinterpret_cast<int *>(smem_raw) + threadIdx.x;
     float *s_t = reinterpret_cast<float *>(smem_raw) + CAND_CAP * TRACE_THREADS + threadIdx.x;
     const int64_t t = (int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x;
-    Counters cn = { 0, 0, 0, 0, 0 };
+    Counters cn = { 0, 0, 0, 0, 0, 0 };
     const bool in_range = t < A.R;
     const int64_t r = in_range ? ray_index(t, P.image_width, P.image_height) : 0;
     float3 o = make_float3(0.f, 0.f, 0.f), d = make_float3(0.f, 0.f, 1.f);
@@ -1253,7 +1252,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, REPLAY ? VP_REPLAY_BLOCKS : VP_
     int *s_id = reinterpret_cast<int *>(smem_raw) + threadIdx.x;
     float *s_t = reinterpret_cast<float *>(smem_raw) + CAND_CAP * TRACE_THREADS + threadIdx.x;
     const int64_t t = (int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x;
-    Counters cn = { 0, 0, 0, 0, 0 };
+    Counters cn = { 0, 0, 0, 0, 0, 0 };
     const bool in_range = t < A.R;
     const int64_t r = in_range ? ray_index(t, P.image_width, P.image_height) : 0;
     float g[3] = { 0.f, 0.f, 0.f };
