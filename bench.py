@@ -11,8 +11,8 @@ collective, so scaling is "weak" and `value` is the sum over ranks.
 Printed JSON (rank 0, one line): the driver contract plus
   roofline     -- k_trace_forward: algorithmic bytes per launch / CUDA-event duration vs measured HBM peak
   cpu_baseline -- the CPU oracle (restatement of the reference loop, C + OpenMP) on a 1/64 pixel subsample
-  e2e          -- the same metric through volprim_balance_b200.render() with the image copied to pinned host
-                  memory inside the timed region
+  e2e          -- the same metric through volprim_balance_b200.render_to_host(): camera host->device, trace, image
+                  device->host into pinned memory, all inside the timed region
 `--impl reference` times the CPU restatement itself (Mitsuba/Dr.Jit cannot be installed here).
 """
 from __future__ import annotations
@@ -337,15 +337,14 @@ def run_ours(args, wl, rank, world, local_rank):
     fwd_adj_ms = f0.elapsed_time(f1) / n_fa
 
     # ---- end to end through the public API: render() + image to pinned host memory ---------------------
-    host_img = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
-    for s in range(2):
-        host_img.copy_(vp.render(scene, sensor=my_view(s), spp=1, jitter=False), non_blocking=True)
+    # render_to_host(): one call for the K views of the timed region; every step's camera goes host->device and every
+    # step's image device->host (pinned ring of two), the copy of view i overlapping the trace of view i+1.
+    host_ring = [torch.empty((H, W, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+    vp.render_to_host(scene, sensors=[my_view(s) for s in range(2)], out=host_ring, spp=1, jitter=False)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for s in range(args.steps):
-        img = vp.render(scene, sensor=my_view(s), spp=1, jitter=False)
-        host_img.copy_(img, non_blocking=True)
+    vp.render_to_host(scene, sensors=[my_view(s) for s in range(args.steps)], out=host_ring, spp=1, jitter=False)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -382,7 +381,7 @@ def run_ours(args, wl, rank, world, local_rank):
         "gpu_launches": args.steps,  # one k_trace_forward launch per step in the timed region
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": cam_bytes,
                 "d2h_bytes_per_step": R * 12, "ms_per_step": e2e_ms / args.steps,
-                "api": "volprim_balance_b200.render(scene, sensor=i, spp=1) -> pinned host image"},
+                "api": "volprim_balance_b200.render_to_host(scene, sensors=[K views], out=<2 pinned images>): camera h2d + trace + image d2h per view, d2h of view i overlapped with the trace of view i+1"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "k_trace_forward<RF,%s,SH3,tile>" % wl.get("kernel", "gaussian").upper(),
                      "algorithmic_bytes_per_launch": sum(algo_bytes) / len(algo_bytes),

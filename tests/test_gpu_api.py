@@ -255,3 +255,34 @@ def test_explicit_ray_batches_nonunit_directions_and_finite_maxt():
     st = compare_forward(res, ref, 64)
     assert 2 < st["mean_hits"] < 40
     print(st)
+
+
+@pytest.mark.gpu
+def test_render_to_host_pipelines_views_and_matches_render():
+    """render_to_host(): the images that land in pinned host memory (copy of view i overlapped with the trace of view
+    i+1, ring of two buffers, consumer callback) are bit-identical to render() of each view."""
+    n = 3000
+    cloud = synthetic.make_cloud(n, synthetic.sigma0_for_hits(n, 12), seed=77, sh_degree=1)
+    cams = [synthetic.ring_camera(i, 8, 64, 32) for i in range(5)]
+    sd = {"type": "scene", "integrator": {"type": "volprim_rf", "max_depth": 64},
+          "primitives": {"type": "ellipsoidsmesh", "centers": cloud.data[:, :3], "scales": cloud.data[:, 3:6],
+                         "quaternions": cloud.data[:, 6:], "opacities": cloud.opacities[:, None],
+                         "sh_coeffs": cloud.sh_coeffs, "extent": 3.0},
+          **{f"sensor_{i}": _sensor_dict(c, "box") for i, c in enumerate(cams)}}
+    scene = vp.load_dict(sd)
+    expected = [vp.render(scene, sensor=i, spp=1, jitter=False).cpu() for i in range(5)]
+    # default: one fresh pinned image per view
+    got = vp.render_to_host(scene, spp=1, jitter=False)
+    assert len(got) == 5 and all(g.is_pinned() and not g.is_cuda for g in got)
+    for e, g in zip(expected, got):
+        assert torch.equal(e, g)
+    # ring of two pinned buffers + consumer callback (the callback sees every image before its buffer is reused)
+    ring = [torch.empty((32, 64, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+    seen = []
+    vp.render_to_host(scene, sensors=[4, 0, 3, 1, 2], out=ring, spp=1, jitter=False,
+                      on_image=lambda i, h: seen.append((i, h.clone())))
+    assert [i for i, _ in seen] == [0, 1, 2, 3, 4]
+    for (i, h), v in zip(seen, [4, 0, 3, 1, 2]):
+        assert torch.equal(h, expected[v])
+    with pytest.raises(Exception):
+        vp.render_to_host(scene, out=ring[:1], spp=1, jitter=False)

@@ -16,7 +16,7 @@ from . import integrators
 from .integrators import ADMode, Ellipsoid, EllipsoidsFactory, Properties, Ray3f
 from . import scene as _scene
 from .scene import (BatchSensor, EllipsoidsShape, PerspectiveSensor, Scene, SceneParameters, load_dict, render,
-                    traverse)
+                    render_to_host, traverse)
 from . import cameras, io, optimizers, utils, synthetic
 
 __version__ = "0.1.0"

@@ -462,3 +462,52 @@ def render(scene: Scene, params=None, sensor=0, integrator=None, seed=0, seed_gr
         img_s = _RenderOp.apply(scene, sensor, integrator, seed, seed_grad, spp, spp_grad, jitter, False, *tensors)
         return torch.where(img_s <= 0.04045, img_s / 12.92, ((img_s.clamp_min(0.04045) + 0.055) / 1.055) ** 2.4)
     return _RenderOp.apply(scene, sensor, integrator, seed, seed_grad, spp, spp_grad, jitter, None, *tensors)
+
+
+def render_to_host(scene: Scene, sensors=None, out=None, integrator=None, seed=0, spp=0, jitter=True, on_image=None):
+    """Render a sequence of sensors and deliver every image in PINNED HOST memory (the loop every caller of the
+    reference writes around `mi.render` + `mi.Bitmap(img)`, e.g. examples/render_3dg_asset.py:76-92).
+
+    The device->host copy of view i runs on a copy stream while view i+1 is traced, so the copy is hidden behind
+    the kernels instead of serialising with them.  `sensors`: indices or sensor objects (default: all sensors of the
+    scene).  `out`: optional list of pinned [H, W, 3] float32 tensors used round-robin (at least two; default: one
+    fresh pinned image per view).  `on_image(i, host_image)` is called once image i is complete in host memory
+    (while later views are in flight).  Returns the list of host images, all complete on return.  Primal only."""
+    integrator = integrator or scene.integrator
+    if not isinstance(integrator, VolprimIntegratorBase):
+        raise Exception("render_to_host: the scene has no volprim integrator")
+    all_sensors = scene.sensors()
+    sensors = list(range(len(all_sensors))) if sensors is None else list(sensors)
+    sensors = [all_sensors[x] if isinstance(x, int) else x for x in sensors]
+    if out is not None and len(out) < 2 and len(sensors) > 1:
+        raise Exception("render_to_host: `out` needs at least two pinned images to overlap copies with rendering")
+    spp = int(spp) if spp else 1
+    main = torch.cuda.current_stream()
+    copier = getattr(scene, '_copy_stream', None)
+    if copier is None:
+        copier = scene._copy_stream = torch.cuda.Stream()
+    results, done = [], []
+    with torch.no_grad():
+        for i, sensor in enumerate(sensors):
+            img = _render_primal(scene, sensor, integrator, seed + i, spp, jitter, record=False)[0]
+            host = out[i % len(out)] if out is not None else torch.empty(img.shape, dtype=img.dtype).pin_memory()
+            if out is not None and i >= len(out):
+                done[i - len(out)].synchronize()       # the buffer's previous image is complete (and was handed to on_image)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            copier.wait_event(ready)
+            with torch.cuda.stream(copier):
+                host.copy_(img, non_blocking=True)
+                img.record_stream(copier)
+                ev = torch.cuda.Event()
+                ev.record(copier)
+            results.append(host)
+            done.append(ev)
+            if on_image is not None and i > 0:
+                done[i - 1].synchronize()
+                on_image(i - 1, results[i - 1])
+    if done:
+        done[-1].synchronize()
+        if on_image is not None:
+            on_image(len(done) - 1, results[-1])
+    return results
