@@ -173,6 +173,34 @@ def test_dense_overlap_falls_back_to_closest_hit_search():
         print(st)
 
 
+def test_far_away_dense_cluster_terminates_and_matches():
+    """A heavily overlapping cluster seen from 2000 units away: the interval width that fits the lists is below one
+    ulp of t there, so `t_start + delta == t_start` in fp32 (regression guard: the walkers must still advance and
+    finish; the closest-hit search takes over).  Both walkers against the oracle."""
+    rng = np.random.default_rng(9)
+    n = 200
+    cloud = synthetic.make_cloud(n, 0.05, seed=9, sh_degree=0)
+    cloud.data[:, 0:3] = rng.normal(0, 0.002, size=(n, 3))
+    cloud.data[:, 3:6] = (0.04 + 0.1 * rng.random((n, 1))) * (1 + 0.2 * rng.random((n, 3)))
+    cloud.opacities[:] = 0.01
+    # an 16x8 pixel bundle of nearly parallel rays from z = -2000 through the cluster
+    ys, xs = np.meshgrid(np.linspace(-0.25, 0.25, 8), np.linspace(-0.35, 0.35, 16), indexing="ij")
+    o = np.stack([xs.ravel(), ys.ravel(), np.full(xs.size, -2000.0)], 1).astype(np.float32)
+    d = np.tile(np.array([[0.0, 0.0, 1.0]], np.float32), (xs.size, 1))
+    mt = np.full(xs.size, np.finfo(np.float32).max, np.float32)
+    acc = gpu_scene(cloud)
+    ref = None
+    for image in (None, (16, 8)):
+        p, op = make_params(0, 0, max_depth=-1, image=image)
+        res = acc.trace_forward(p, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt), record_cap=256)
+        torch.cuda.synchronize()
+        ref = ref or oracle_scene(cloud).forward(op, o, d, mt, cap=256, fragility=True)
+        assert ref.nhits.max() > 50
+        st = compare_forward(res, ref, 256, max_fragile_frac=1.0)   # at t = 2000 most lists are fragile; robust ones must match
+        print(st)
+        assert acc.stats()["stack_overflows"] == 0
+
+
 def test_tile_walker_fallback_does_not_disturb_neighbour_warps():
     """Coarse image over a dense cloud: tiles are wide, their candidate lists overflow and single warps hand over to
     the per-ray walker while the other warps of the block keep using their shared-memory queues (regression: the

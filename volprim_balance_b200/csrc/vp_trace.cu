@@ -270,8 +270,14 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
     int closest_left = 0;
     int stack[STACK_MAX];
     while (__any_sync(0xffffffffu, alive)) {
-        const float t_lo = strict_lo ? t_start : t_start - (1e-4f + 1e-5f * t_start);
-        float t_end = (S.root >= 0 && !closest_mode) ? t_start + delta : VP_INF;
+        // Entries are re-listed from a little before t_start (the ordering test's rounding error grows with t).  An
+        // interval shorter than that look-back would list the same stale entries again and again and crawl (seen with a
+        // dense cluster 2000 units from the camera), hence the floor on the interval width.
+        const float slack = 1e-4f + 1e-5f * t_start;
+        const float t_lo = strict_lo ? t_start : t_start - slack;
+        const float delta_floor = fmaxf(delta_min, 2.f * slack);
+        // (the max keeps the interval from collapsing to nothing when delta is below one ulp of a large t_start)
+        float t_end = (S.root >= 0 && !closest_mode) ? fmaxf(t_start + delta, t_start * 1.000001f) : VP_INF;
         int n_c = 0;
         bool overflow = false;
         float best_t = VP_INF;
@@ -349,7 +355,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
         }
         __syncwarp();
         // ---- phase 2: entry distances; keep the entries inside the interval ----
-        int n_h = 0;
+        int n_h = 0, n_new = 0;   // n_new: entries beyond t_start (the look-back ones do not count for the width)
         if (closest_mode) {
             if (best_pos >= 0) { s_id[0] = best_pos; s_t[0] = best_t; n_h = 1; }
         } else if (!overflow) {
@@ -362,6 +368,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
                 if (ok && tn > t_lo && tn <= t_end) {
                     list_insert<STRIDE>(s_id, s_t, n_h, tn, pos);   // n_h <= k: entry k is already read
                     ++n_h;
+                    n_new += tn > t_start ? 1 : 0;
                 }
             }
             cn.candidates += n_c;
@@ -375,18 +382,18 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
             if (S.root < 0) { missed = true; alive = false; }
             else if (overflow) {
                 delta *= 0.5f;
-                if (delta < delta_min) { closest_mode = true; closest_left = 8; }
+                if (delta < delta_floor) { closest_mode = true; closest_left = 8; }
             } else if (closest_mode) {
                 if (best_pos < 0) { missed = true; alive = false; }   // nothing in front of t_start at all
                 else {
                     t_start = best_t;      // strictly beyond the entry just handled
                     strict_lo = true;
-                    if (--closest_left <= 0) { closest_mode = false; delta = delta_min * 8.f; }
+                    if (--closest_left <= 0) { closest_mode = false; delta = delta_floor * 8.f; }
                 }
             } else {
                 strict_lo = false;
                 t_start = t_end;
-                delta *= (n_found == 0) ? 4.f : fminf(fmaxf((float)TARGET_HITS / (float)n_found, 0.5f), 2.f);
+                delta = fmaxf(delta * ((n_new == 0) ? 4.f : fminf(fmaxf((float)TARGET_HITS / (float)n_new, 0.5f), 2.f)), delta_floor);
             }
             if (alive && t_start > t_stop) { missed = true; alive = false; }
         }
@@ -629,8 +636,8 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
     while (true) {
         const unsigned am = __ballot_sync(FULL, alive);
         if (!am) break;
-        const float t_lo = t_start - (1e-4f + 1e-5f * t_start);
-        const float t_end = t_start + delta;
+        const float t_lo = t_start - (1e-4f + 1e-5f * t_start);   // look-back and width floor: see walk_ray
+        const float t_end = fmaxf(t_start + delta, t_start * 1.000001f);   // progress even below one ulp of t_start
         if (alive) cn.passes++;
         const Capsule cap = tile_capsule(alive, am, o0, d, t_lo, t_end);
         // ---- phase 1 (cooperative): 32 queued nodes per step against the interval's capsule ----
@@ -720,7 +727,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         if (overflow) {   // the tile's candidate list or the node queue did not fit: shorter interval, walk again
             if (alive) cn.retries++;   // (statistics)
             delta *= VP_OVF_SHRINK;
-            if (delta < delta_min) {   // cannot be listed: the per-ray walker has the closest-hit fallback
+            if (delta < fmaxf(delta_min, 2.f * (t_start - t_lo))) {   // cannot be listed: the per-ray walker has the closest-hit fallback
                 t_hand = t_start;
                 return true;
             }
@@ -751,7 +758,8 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         // the interval grows or shrinks so that the fullest of the lists it has to fit -- the busiest lane's hit list
         // and the tile's candidate list -- lands at VP_FILL of its capacity; after a cut it restarts from the width
         // that actually fitted
-        if (t_done < t_end) delta = fmaxf((t_done - t_start) * 0.75f, delta_min);
+        const float delta_floor = fmaxf(delta_min, 2e-4f + 2e-5f * t_start);   // twice the look-back
+        if (t_done < t_end) delta = fmaxf((t_done - t_start) * 0.75f, delta_floor);
         else {
             const float fill_h = (float)found_max * (1.f / (VP_FILL * TILE_HIT_CAP));
             const float fill_c = (float)tcn * (1.f / (float)(VP_CAND_TARGET));
@@ -759,7 +767,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
             // the candidate count only shrinks the interval while that can help: boxes that contain the whole
             // neighbourhood (nested primitives) stay candidates however short the interval gets
             const float f_c = fmaxf(1.f / fmaxf(fill_c, 0.25f), delta > delta0 * (1.f / VP_CSHRINK_FLOOR) ? 0.5f : 1.f);
-            delta = fmaxf(delta * fminf(f_h, f_c), delta_min);
+            delta = fmaxf(delta * fminf(f_h, f_c), delta_floor);
         }
         t_start = t_done;
         if (alive && t_start > t_out) { missed = true; alive = false; }
@@ -777,6 +785,33 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         walk_ray<TILE_FALLBACK_CAP, 2 * TRACE_THREADS>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit, t_hand);
         missed = missed || m2;
     }
+}
+
+// Origin the walkers measure their interval distances from.  Ordinarily the ray origin itself; for a camera far outside
+// the scene (more than 8 box diagonals away) a point just before the scene box, so that the fp32 resolution of the
+// ordering distances is that of the scene, not of the camera distance.  Warp-uniform shift for the tile walker (its
+// intervals are shared by the 32 lanes).  Only ordering / culling use it: hits are accepted by the exact test against
+// the ray's true, re-based origin.
+template <bool TILE>
+__device__ __forceinline__ float3 walker_origin(const DevScene &S, float3 o, float3 d, bool alive)
+{
+    if (S.n <= 0 || S.root < 0) return o;
+    const float3 lo = make_float3(__ldg(S.info), __ldg(S.info + 1), __ldg(S.info + 2));
+    const float3 hi = make_float3(__ldg(S.info + 3), __ldg(S.info + 4), __ldg(S.info + 5));
+    const float ix = 1.f / (fabsf(d.x) > 1e-30f ? d.x : copysignf(1e-30f, d.x));
+    const float iy = 1.f / (fabsf(d.y) > 1e-30f ? d.y : copysignf(1e-30f, d.y));
+    const float iz = 1.f / (fabsf(d.z) > 1e-30f ? d.z : copysignf(1e-30f, d.z));
+    const float ax = (lo.x - o.x) * ix, bx = (hi.x - o.x) * ix, ay = (lo.y - o.y) * iy, by = (hi.y - o.y) * iy;
+    const float az = (lo.z - o.z) * iz, bz = (hi.z - o.z) * iz;
+    float t_in = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+    const float t_ex = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    if (!alive || !(t_in <= t_ex)) t_in = VP_INF;                // misses the box: no say in the shift
+    if (TILE) for (int off = 16; off; off >>= 1) t_in = fminf(t_in, __shfl_xor_sync(0xffffffffu, t_in, off));
+    const float dlen = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+    const float diag = sqrtf((hi.x - lo.x) * (hi.x - lo.x) + (hi.y - lo.y) * (hi.y - lo.y) + (hi.z - lo.z) * (hi.z - lo.z));
+    if (!(t_in < VP_INF) || !(t_in * dlen > 8.f * diag)) return o;
+    const float shift = t_in - diag / fmaxf(dlen, 1e-30f);      // one diagonal before the box
+    return make_float3(fmaf(d.x, shift, o.x), fmaf(d.y, shift, o.y), fmaf(d.z, shift, o.z));
 }
 
 // ---- closed-form primitive evaluation --------------------------------------------------------
@@ -996,7 +1031,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
         d = make_float3(A.d[3 * r], A.d[3 * r + 1], A.d[3 * r + 2]);
         if (A.maxt) maxt = A.maxt[r];
     }
-    const float3 o0 = o;
+    const float3 o0 = walker_origin<TILE>(S, o, d, in_range);
     float beta = 1.f, L[3] = { 0.f, 0.f, 0.f };
     uint32_t depth = 0;
     bool missed = false;
@@ -1267,7 +1302,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, REPLAY ? VP_REPLAY_BLOCKS : VP_
         if (A.maxt) maxt = A.maxt[r];
         L[0] = A.state_in[3 * r]; L[1] = A.state_in[3 * r + 1]; L[2] = A.state_in[3 * r + 2];
     }
-    const float3 o0 = o;
+    float3 o0 = o;
+    if constexpr (!REPLAY) o0 = walker_origin<TILE>(S, o, d, alive);
     float beta = 1.f;
     uint32_t depth = 0;
     constexpr int NY = (D >= 0) ? (D + 1) * (D + 1) : 1;
