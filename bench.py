@@ -319,10 +319,16 @@ def run_ours(args, wl, rank, world, local_rank):
     gbuf = (torch.zeros(cloud.n * 10, device=dev), torch.zeros(cloud.n, device=dev),
             torch.zeros(cloud.n * cloud.sh_coeffs.shape[1], device=dev))
 
+    adj_ev = []
+
     def step_fwd_adj(step):
         o, d, mt = rays[my_view(step)]
         r = acc.trace_forward(params, o, d, mt, record_cap=fa_cap)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
         acc.trace_adjoint(params, o, d, mt, dL, r.rgb, r.hit_ids, r.nhits, out=gbuf)
+        a1.record()
+        adj_ev.append((a0, a1, my_view(step)))
 
     fa_cap = 128 if wl.get("max_depth", 128) > 0 else 512
     step_fwd_adj(0)
@@ -335,6 +341,11 @@ def run_ours(args, wl, rank, world, local_rank):
     f1.record()
     barrier()
     fwd_adj_ms = f0.elapsed_time(f1) / n_fa
+    # adjoint kernel alone (replay of the recorded hit lists): SURVEY 8(d) counts 708 B per evaluation at SH3 (forward
+    # read + gradient read-modify-write) + 68 B per ray; the gradient traffic is absorbed by the L2 reduction units
+    adj_ms = [a.elapsed_time(b) for a, b, _ in adj_ev[-n_fa:]]
+    adj_bytes = [R * (RAY_IO_BYTES + 24) + hits_per_view[v] * 3 * EVAL_BYTES_SH3 for _, _, v in adj_ev[-n_fa:]]
+    adj_gbs = sum(adj_bytes) / (sum(adj_ms) * 1e-3) / 1e9
 
     # ---- end to end through the public API: render() + image to pinned host memory ---------------------
     # render_to_host(): one call for the K views of the timed region; every step's camera goes host->device and every
@@ -388,6 +399,10 @@ def run_ours(args, wl, rank, world, local_rank):
                      "kernel_ms": sum(kern_ms) / len(kern_ms), "peak_source": peak_src},
         "primitive_evals_per_s": mean_hits * R * args.steps * world / (total_ms * 1e-3),
         "fwd_adjoint_ms_per_view": fwd_adj_ms,
+        "adjoint": {"kernel": "k_trace_adjoint<replay>", "kernel_ms": sum(adj_ms) / len(adj_ms),
+                    "algorithmic_bytes_per_launch": sum(adj_bytes) / len(adj_bytes), "achieved": adj_gbs, "unit": "GB/s",
+                    "frac": adj_gbs / peak, "note": "gradient read-modify-write is served by the L2 reduction units, "
+                    "not HBM; the fraction can therefore exceed what DRAM alone would allow"},
     }
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof) and args.workload == "cfg2":
