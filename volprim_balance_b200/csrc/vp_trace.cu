@@ -4,23 +4,26 @@
 // (Primal/Backward)" together with the scene.ray_intersect() they call once per hit
 // (reference: volprim/integrators/volprim_rf.py:103-192, volprim_tomography.py:47-127).
 //
-// Algorithm (one thread per ray, rays walked in 8x4 pixel tiles per warp, loops warp-uniform):
-//   The ray is cut into consecutive intervals [t_start, t_start + delta] (delta adapts per ray so that an
-//   interval holds about a dozen entries).  Per interval:
-//   phase 1 (collect)  stack traversal of the LBVH restricted to the interval; leaves are only APPENDED to a
-//                      per-thread candidate list in shared memory.  No test result feeds back into the walk, so
-//                      the 32 lanes of a warp stay in the node loop together (the per-lane k-buffer version
-//                      measured 7 active lanes of 32 here);
-//   phase 2 (test)     every candidate gets the ray/ellipsoid entry distance from the pre-transformed SoA
-//                      record (48 B); entries inside the interval stay in the list;
-//   phase 3 (drain)    entries are taken in increasing distance; each is RE-EVALUATED against the current,
-//                      re-based origin with the same fixed-order fp32 arithmetic as the parity oracle.  This
-//                      applies the reference's "advance the origin by 1e-4 and query again with back-face
-//                      culling" rule exactly (entries that fell behind the advanced origin are dropped, SURVEY
-//                      quirk Q1) and keeps the origin bit-identical to the one the reference loop carries.
-//   The ray stops on leaving the scene box (miss), max_depth, or (rf) beta <= t_cutoff.  If one interval holds
-//   more candidates than the list (pathological overlap) the interval is halved; below a minimum width the lane
-//   falls back to a plain closest-hit walk for that step.
+// Algorithm (one thread per ray; loops warp-uniform).  The ray is cut into consecutive intervals [t_start, t_start +
+// delta]; delta adapts so that the lists below fill to ~70 % (tile walker) / hold about ten entries (per-ray walker).
+//   phase 1   (collect)  LBVH walk restricted to the interval; leaves are only APPENDED to a candidate list in shared
+//                        memory.  No test result feeds back into the walk (the per-lane k-buffer version measured 7
+//                        active lanes of 32 here).  Tile walker (image-shaped launches, a warp = an 8x4 pixel tile):
+//                        ONE walk per warp -- 32 queued nodes per step are tested by the 32 lanes against a capsule
+//                        around the tile's ray segments.  Per-ray walker (explicit ray batches, and what a tile hands
+//                        over to when its rays are incoherent): branch-free stack traversal per lane.
+//   phase 1.5 (cull)     tile walker only: one candidate per lane against the tile's ray bundle in the primitive's
+//                        unit-sphere space; more than half of the box-level candidates are touched by no ray.
+//   phase 2   (test)     every candidate gets the ray/ellipsoid entry distance from the pre-transformed SoA record
+//                        (48 B); entries inside the interval go to a per-lane list sorted by distance;
+//   phase 3   (drain)    entries are taken in increasing distance; each is RE-EVALUATED against the current, re-based
+//                        origin with the same fixed-order fp32 arithmetic as the parity oracle.  This applies the
+//                        reference's "advance the origin by 1e-4 and query again with back-face culling" rule exactly
+//                        (entries that fell behind the advanced origin are dropped) and keeps the
+//                        origin bit-identical to the one the reference loop carries.
+//   The ray stops on leaving the scene box (miss), max_depth, or (rf) beta <= t_cutoff.  A tile whose lane lists fill
+//   up ends the interval at the nearest full lane's farthest entry (nothing is walked twice); candidate-list overflows
+//   retry with a shorter interval; below a minimum width the per-ray walker runs a plain closest-hit search per step.
 // The adjoint either replays recorded hit lists (no BVH access) or re-traces like the primal.
 #include "vp_internal.cuh"
 
@@ -45,17 +48,18 @@ constexpr int TRACE_THREADS = 128;
 constexpr int NODE_SENTINEL = 0x7fffffff;
 constexpr size_t TRACE_SMEM = (size_t)CAND_CAP * TRACE_THREADS * 8;
 // warp-cooperative (tile) walker: per-lane hit lists + per-warp node queue and tile candidate list
+// (tunables; the values are the measured optimum over cfg2 / cfg3 / cfg5, see DESIGN.md sections 7-8)
 #ifndef VP_FILL
-#define VP_FILL 0.7f
+#define VP_FILL 0.7f            // interval width aims at this fill of the fullest list
 #endif
 #ifndef VP_OVF_SHRINK
-#define VP_OVF_SHRINK 0.35f
+#define VP_OVF_SHRINK 0.35f     // width factor after a candidate-list / queue overflow
 #endif
 #ifndef VP_GROW_MAX
-#define VP_GROW_MAX 2.f
+#define VP_GROW_MAX 2.f         // largest growth of the width from one interval to the next
 #endif
 #ifndef VP_CSHRINK_FLOOR
-#define VP_CSHRINK_FLOOR 32.f
+#define VP_CSHRINK_FLOOR 32.f   // the candidate count stops shrinking the width below delta0 / this
 #endif
 #ifndef VP_CAND_TARGET
 #define VP_CAND_TARGET (VP_FILL * VP_TILE_CCAP)
@@ -774,12 +778,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
     }
     return false;
     };
-#ifdef VP_EXP_NO_FALLBACK
-    tile_part();
-    if (false) {
-#else
     if (tile_part()) {
-#endif
         bool m2 = false;   // lanes that missed the scene box keep their `missed`
         __syncwarp();
         walk_ray<TILE_FALLBACK_CAP, 2 * TRACE_THREADS>(S, fb_id, fb_t, o, o0, d, maxt, alive, m2, cn, on_hit, t_hand);
