@@ -286,3 +286,42 @@ def test_render_to_host_pipelines_views_and_matches_render():
         assert torch.equal(h, expected[v])
     with pytest.raises(Exception):
         vp.render_to_host(scene, out=ring[:1], spp=1, jitter=False)
+
+
+@pytest.mark.gpu
+def test_backward_replaying_the_primal_records_equals_rerendering():
+    """render() keeps the primal's hit lists for the backward pass when the gradient pass would draw the same samples;
+    the gradients must equal those of the reference's scheme (render the primal again, RBIntegrator.render_backward),
+    for pixel-centre samples and for jittered samples with seed_grad == seed."""
+    from volprim_balance_b200 import scene as scene_mod
+    n = 4000
+    cloud = synthetic.make_cloud(n, synthetic.sigma0_for_hits(n, 14), seed=41, sh_degree=2)
+    cam = synthetic.ring_camera(2, 8, 64, 32)
+    sd = {"type": "scene", "integrator": {"type": "volprim_rf", "max_depth": 64},
+          "primitives": {"type": "ellipsoidsmesh", "centers": cloud.data[:, :3], "scales": cloud.data[:, 3:6],
+                         "quaternions": cloud.data[:, 6:], "opacities": cloud.opacities[:, None],
+                         "sh_coeffs": cloud.sh_coeffs, "extent": 3.0},
+          "sensor": _sensor_dict(cam, "box")}
+    w = torch.from_numpy(np.random.default_rng(2).normal(size=(32, 64, 3)).astype(np.float32)).cuda()
+    keys = ("primitives.data", "primitives.opacities", "primitives.sh_coeffs")
+
+    def grads(reuse, **kw):
+        scene = vp.load_dict(sd)
+        params = vp.traverse(scene)
+        for k in keys:
+            params[k].requires_grad_(True)
+        scene_mod.REUSE_PRIMAL_RECORDS = reuse
+        try:
+            img = vp.render(scene, params, sensor=0, **kw)
+            (img * w).sum().backward()
+        finally:
+            scene_mod.REUSE_PRIMAL_RECORDS = True
+        return img.detach(), [params[k].grad.clone() for k in keys]
+
+    for kw in (dict(spp=1, jitter=False), dict(spp=2, seed=5, seed_grad=5, jitter=True)):
+        img_a, g_a = grads(True, **kw)
+        img_b, g_b = grads(False, **kw)
+        assert torch.equal(img_a, img_b)
+        for a, b, k in zip(g_a, g_b, keys):
+            grad_close(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, what=k)
+            assert float(b.abs().max()) > 0

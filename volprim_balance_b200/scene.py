@@ -321,14 +321,27 @@ def _film_weights(sensor_w, H, spp, jit, rfilter, device):
     return torch.stack(idx, 1), torch.stack(wts, 1)
 
 
+REUSE_PRIMAL_RECORDS = True   # False: always re-render the primal in the backward pass, as RBIntegrator does
+
+
 class _RenderOp(torch.autograd.Function):
     """mi.render as a differentiable op: forward = primal render, backward = RBIntegrator.render_backward
     (re-render the primal with the gradient seed, then the adjoint pass)."""
 
     @staticmethod
     def forward(ctx, scene, sensor, integrator, seed, seed_grad, spp, spp_grad, jitter, srgb, *tensors):
-        img, _ = _render_primal(scene, sensor, integrator, seed, spp, jitter, record=False, srgb=srgb)
-        ctx.args = (scene, sensor, integrator, seed_grad, spp_grad or spp, jitter, srgb)
+        # When the gradient pass would draw exactly the primal's samples (pixel centres, or the same seed and spp), the
+        # primal records its hit lists and the backward pass replays them instead of rendering the primal a second
+        # time (a third of the step in examples/refine_3dg_dataset.py).  Records above 2 GiB per view are not kept.
+        spp_g = spp_grad or spp
+        same_samples = spp_g == spp and (not jitter or seed_grad == seed)
+        views, _ = _views(sensor)
+        cap = integrator._cap()
+        fits = all(v.width * v.height * spp * cap * 4 <= (2 << 30) for v in views)
+        keep = same_samples and fits and REUSE_PRIMAL_RECORDS
+        img, aux = _render_primal(scene, sensor, integrator, seed, spp, jitter, record=keep, srgb=srgb)
+        ctx.args = (scene, sensor, integrator, seed_grad, spp_g, jitter, srgb)
+        ctx.aux = aux if keep else None
         ctx.n_tensors = len(tensors)
         return img
 
@@ -337,7 +350,8 @@ class _RenderOp(torch.autograd.Function):
         scene, sensor, integrator, seed_grad, spp_grad, jitter, srgb = ctx.args
         shape = scene.ellipsoids()
         shape.zero_grad()
-        _render_adjoint(scene, sensor, integrator, seed_grad, spp_grad, jitter, grad_img.contiguous(), srgb)
+        _render_adjoint(scene, sensor, integrator, seed_grad, spp_grad, jitter, grad_img.contiguous(), srgb, aux=ctx.aux)
+        ctx.aux = None
         out = []
         for name in _differentiable_names(shape, integrator):
             g = shape.grad.get(name)
@@ -405,12 +419,13 @@ def _render_primal_impl(scene, sensor, integrator, seed, spp, jitter, record):
     return (images[0] if len(images) == 1 else torch.cat(images, dim=1)), aux
 
 
-def _render_adjoint(scene, sensor, integrator, seed, spp, jitter, grad_img, srgb=None):
+def _render_adjoint(scene, sensor, integrator, seed, spp, jitter, grad_img, srgb=None, aux=None):
     """RBIntegrator.render_backward: primal with the gradient seed, then sample(Backward) with state_in = the
     primal's state_out (volprim_rf.py:192) -- which, with srgb_primitives, is the LINEAR radiance fed into an
     sRGB-space recursion (reference quirk Q3, reproduced when srgb is left at the plugin's own value)."""
     views, _ = _views(sensor)
-    _, aux = _render_primal(scene, sensor, integrator, seed, spp, jitter, record=True, srgb=srgb)
+    if aux is None:
+        _, aux = _render_primal(scene, sensor, integrator, seed, spp, jitter, record=True, srgb=srgb)
     x0 = 0
     with _srgb_override(integrator, srgb):
         for s, (o, d, maxt, state, idx, w, wsum, image_hint, last) in zip(views, aux):
@@ -423,7 +438,14 @@ def _render_adjoint(scene, sensor, integrator, seed, spp, jitter, grad_img, srgb
                 dL = torch.zeros((idx.shape[0], 3), device=g.device)
                 for k in range(idx.shape[1]):
                     dL += g[idx[:, k]] * (w[:, k] / wsum.clamp_min(1e-12)[idx[:, k]])[:, None]
-            full = bool((last.nhits <= last.hit_ids.shape[0]).all()) if last.hit_ids is not None else False
+            # the recorded lists can be replayed if every ray's list fits the record; with max_depth <= cap that holds
+            # by construction and needs no device->host check (which would stall the launch queue once per view)
+            if last.hit_ids is None:
+                full = False
+            elif int(integrator.max_depth) <= last.hit_ids.shape[0]:
+                full = True
+            else:
+                full = bool((last.nhits <= last.hit_ids.shape[0]).all())
             integrator.sample(ADMode.Backward, scene, None, Ray3f(o, d, maxt), dL.contiguous(), state, True,
                               image=image_hint, hit_ids=last.hit_ids if full else None,
                               hit_counts=last.nhits if full else None)
