@@ -173,6 +173,25 @@ def test_dense_overlap_falls_back_to_closest_hit_search():
         print(st)
 
 
+def test_sparse_tiny_primitives_long_intervals():
+    """Tiny primitives in a large box: intervals are thousands of primitive radii long, most rays graze or miss.  The
+    tile walker's candidate cull works in each primitive's unit-sphere space, where such a segment start lies thousands
+    of units from the origin -- its rounding margin must not reject grazing hits.  Hit lists against the oracle."""
+    n = 30000
+    cloud = synthetic.make_cloud(n, 2e-3, seed=12, sh_degree=0)
+    cloud.opacities[:] = 0.5
+    o, d, mt = _rays(view=1, w=128, h=64)
+    acc = gpu_scene(cloud)
+    ref = None
+    for image in (None, (128, 64)):
+        p, op = make_params(0, 0, max_depth=64, image=image)
+        res = acc.trace_forward(p, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt), record_cap=16)
+        ref = ref or oracle_scene(cloud).forward(op, o, d, mt, cap=16, fragility=True)
+        st = compare_forward(res, ref, 16)
+        assert 0.2 < st["mean_hits"] < 5 and st["robust"] > 0.9 * st["rays"]
+        print(st)
+
+
 def test_far_away_dense_cluster_terminates_and_matches():
     """A heavily overlapping cluster seen from 2000 units away: the interval width that fits the lists is below one
     ulp of t there, so `t_start + delta == t_start` in fp32 (regression guard: the walkers must still advance and

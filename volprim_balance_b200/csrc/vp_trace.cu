@@ -521,7 +521,9 @@ __device__ __forceinline__ bool prism_may_hit(const DevScene &S, int pos, const 
                                  r0.z * e.x + r1.z * e.y + r2.z * e.z);
     const float h = p.ra * fabsf(g.x * p.u.x + g.y * p.u.y + g.z * p.u.z) + p.rb * fabsf(g.x * p.v.x + g.y * p.v.y + g.z * p.v.z)
                   + p.rw * fabsf(g.x * p.w.x + g.y * p.w.y + g.z * p.w.z);
-    return !(pl > 1.002f + 1.002f * h);
+    // rounding of P = A' - k D' grows with |A'| (long intervals over tiny primitives): widen the margin accordingly
+    const float err = 2e-6f * (fabsf(Ap.x) + fabsf(Ap.y) + fabsf(Ap.z));
+    return !(pl > 1.002f + 1.002f * h + err);
 }
 
 // child boxes of one node against a capsule
