@@ -67,8 +67,10 @@ constexpr size_t TRACE_SMEM = (size_t)CAND_CAP * TRACE_THREADS * 8;
 #ifndef VP_TILE_HIT_CAP
 #define VP_TILE_HIT_CAP 24
 #endif
+// 24 x 128 x 8 B of lists + 4 x (224 + 192) x 4 B of queues = 30.5 KB per block: six blocks fit the 196 KB shared-memory
+// carve-out, which leaves the SM 60 KB of L1 instead of 28 KB (cfg2 / cfg3 -2 %; a 512-entry queue was never needed)
 #ifndef VP_TILE_QCAP
-#define VP_TILE_QCAP 512
+#define VP_TILE_QCAP 224
 #endif
 #ifndef VP_TILE_CCAP
 #define VP_TILE_CCAP 192
