@@ -28,6 +28,13 @@ hdr, units, vals = r[0], r[1], r[2]
 get = lambda name: next((f"{vals[i]} {units[i]}" for i, x in enumerate(hdr) if x == name), "n/a")
 num = lambda name: next((float(vals[i].replace(',', '')) for i, x in enumerate(hdr) if x == name), None)
 out.append(f"\n## Top kernel counters (`{os.path.basename(rep)}`, one launch of `{vals[hdr.index('Kernel Name')][:60]}`)\n")
+out.append("Captured with `ncu --section SourceCounters --section WarpStateStats --section SchedulerStats --section Occupancy "
+           "--section LaunchStats --section MemoryWorkloadAnalysis --section SpeedOfLight --metrics "
+           "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --import-source on "
+           "-k regex:k_trace_forward -s 3 -c 1` on `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (after the same "
+           "command had exited 0 without ncu).  The section list replaces `--set full` because a full-set capture of this "
+           "kernel takes ≈8 GPU-minutes of the round's budget (done once earlier in the round: same DRAM traffic, 0.39 GB per "
+           "launch); the DRAM byte counters are requested explicitly.\n")
 for m in ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
           "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.per_cycle_active",
           "smsp__thread_inst_executed_per_inst_executed.ratio", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
