@@ -79,6 +79,7 @@ constexpr int TILE_HIT_CAP = VP_TILE_HIT_CAP;
 constexpr int TILE_QCAP = VP_TILE_QCAP;
 constexpr int TILE_CCAP = VP_TILE_CCAP;
 constexpr size_t TILE_SMEM = (size_t)TILE_HIT_CAP * TRACE_THREADS * 8 + (size_t)(TRACE_THREADS / 32) * (TILE_QCAP + TILE_CCAP) * 4;
+static_assert(TILE_QCAP >= TILE_CCAP, "the idle node queue holds two of the three candidate buckets");
 constexpr int TILE_FALLBACK_CAP = TILE_HIT_CAP;  // the per-ray fallback may only touch the warp's OWN list columns
 #define VP_INF __int_as_float(0x7f800000)
 #ifdef VP_DEBUG_CHECKS   // bounds checks for debugging builds (compute-sanitizer is not available on the GPU pool)
@@ -502,8 +503,9 @@ __device__ __forceinline__ TilePrism tile_prism(bool alive, unsigned am, float3 
 // c), the record fast_isect uses) the mean line passes the origin at distance |P|, P = A' - (A'.D^)D^.  Along e = P/|P|
 // a point of the prism lies at e.x' = |P| + g.q with g = M^T e and q the deviation, |g.q| <= ra|g.u| + rb|g.v| + rw|g.w|.
 // If that cannot come down to 1 no ray of the tile reaches the ellipsoid.  Conservative: never rejects a real hit.
-__device__ __forceinline__ bool prism_may_hit(const DevScene &S, int pos, const TilePrism &p)
+__device__ __forceinline__ bool prism_may_hit(const DevScene &S, int pos, const TilePrism &p, float &lam)
 {
+    lam = 0.f;   // where the mean line enters the ellipsoid (or passes closest), as a fraction of the segment
     const float4 *x = S.xf + 3ll * pos;
     const float4 r0 = __ldg(x), r1 = __ldg(x + 1), r2 = __ldg(x + 2);
     const float3 a = make_float3(p.A.x - r0.w, p.A.y - r1.w, p.A.z - r2.w);
@@ -516,7 +518,11 @@ __device__ __forceinline__ bool prism_may_hit(const DevScene &S, int pos, const 
     const float k = (Ap.x * Dp.x + Ap.y * Dp.y + Ap.z * Dp.z) / dd;
     const float3 P = make_float3(Ap.x - k * Dp.x, Ap.y - k * Dp.y, Ap.z - k * Dp.z);
     const float pl2 = P.x * P.x + P.y * P.y + P.z * P.z;
-    if (!(pl2 > 1.f)) return true;          // the mean line itself passes through the bounding ellipsoid
+    lam = -k;
+    if (!(pl2 > 1.f)) {                     // the mean line itself passes through the bounding ellipsoid
+        lam -= sqrtf((1.f - pl2) / dd);
+        return true;
+    }
     const float ipl = rsqrtf(pl2), pl = pl2 * ipl;
     const float3 e = make_float3(P.x * ipl, P.y * ipl, P.z * ipl);
     const float3 g = make_float3(r0.x * e.x + r1.x * e.y + r2.x * e.z, r0.y * e.x + r1.y * e.y + r2.y * e.z,
@@ -682,25 +688,33 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
             __syncwarp();
         }
         __syncwarp();
-#ifndef VP_NO_PRISM_CULL
         // ---- phase 1.5: lane-parallel cull of the candidates no ray of the tile can touch (more than half of what
         // the box-vs-capsule walk lists: rotated anisotropic ellipsoids fill little of their boxes).  One candidate
         // per lane, compacted in place; costs ~3 issue slots per candidate, phase 2 costs ~50 per surviving one. ----
+        int n_b0 = tcn, n_b1 = 0, n_b2 = 0;
         if (!overflow && tcn > 0) {
             const TilePrism pr = tile_prism(alive, am, o0, d, t_lo, t_end);
+            // The survivors are split into three buckets by where the tile's mean line meets them (near third of the
+            // interval: compacted in place; middle: front of the now idle node queue; far: back of it) and phase 2
+            // visits the buckets in that order, so the per-lane sorted insertions mostly land near the list tail.
             int kept = 0;
+            n_b1 = 0; n_b2 = 0;
             for (int k0 = 0; k0 < tcn; k0 += 32) {
                 const int k = k0 + lane;
                 const int pos = k < tcn ? w_cand[k] : -1;
-                const bool keep = pos >= 0 && prism_may_hit(S, pos, pr);
-                const unsigned mk = __ballot_sync(FULL, keep);
-                if (keep) w_cand[kept + __popc(mk & lt)] = pos;   // kept <= k0: never ahead of the reads
-                kept += __popc(mk);
+                float lam;
+                const bool keep = pos >= 0 && prism_may_hit(S, pos, pr, lam);
+                const bool b0 = keep && lam < (1.f / 3.f), b2 = keep && lam >= (2.f / 3.f), b1 = keep && !b0 && !b2;
+                const unsigned m0 = __ballot_sync(FULL, b0), m1 = __ballot_sync(FULL, b1), m2 = __ballot_sync(FULL, b2);
+                if (b0) w_cand[kept + __popc(m0 & lt)] = pos;   // kept <= k0: never ahead of the reads
+                if (b1) w_queue[n_b1 + __popc(m1 & lt)] = pos;
+                if (b2) w_queue[TILE_QCAP - 1 - (n_b2 + __popc(m2 & lt))] = pos;
+                kept += __popc(m0); n_b1 += __popc(m1); n_b2 += __popc(m2);
                 __syncwarp();
             }
-            tcn = kept;
+            n_b0 = kept;
+            tcn = kept + n_b1 + n_b2;
         }
-#endif
         // ---- phase 2: every lane tests the tile's candidates against its own ray ----
         // (warp-uniform loop, broadcast loads; four candidates per trip so that their loads overlap)
         int n_h = 0;
@@ -711,7 +725,13 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
                 float tn[4];
                 bool ok[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pos[u] = w_cand[k0 + u < tcn ? k0 + u : k0];
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = k0 + u < tcn ? k0 + u : k0;
+                    const int *src = idx < n_b0 ? w_cand + idx
+                                                : (idx < n_b0 + n_b1 ? w_queue + (idx - n_b0)
+                                                                     : w_queue + (TILE_QCAP - 1 - (idx - n_b0 - n_b1)));
+                    pos[u] = *src;
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) ok[u] = fast_isect(S, pos[u], o0, d, tn[u]);
 #pragma unroll
