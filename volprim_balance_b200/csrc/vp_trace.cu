@@ -227,11 +227,12 @@ __device__ __forceinline__ void drain_list(const DevScene &S, int n_found, GetPo
                                            const float3 d, float maxt, bool &alive, bool &missed, OnHit &&on_hit)
 {
     VP_CHECK(n_found >= 0 && n_found <= 64, 5, n_found, 0);
-    if (alive && n_found > 0) prefetch_prim(S, get_pos(0));
+    // (no prefetch of entry k + 1 here: with ~200 KB of the SM's 256 KB given to shared memory the 768 resident
+    // threads' prefetched lines evict each other from L1 before they are used -- measured +2 % time; the replay
+    // adjoint, which uses no shared memory, keeps its software pipeline)
     for (int k = 0; alive && k < n_found; ++k) {
         const int pos = get_pos(k);
         VP_CHECK(pos >= 0 && pos < S.n, 6, pos, k);
-        if (k + 1 < n_found) prefetch_prim(S, get_pos(k + 1));
         float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
         Mat3 Rm = vp_quat_to_matrix_rn(g2);
         Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
