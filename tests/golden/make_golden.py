@@ -71,12 +71,17 @@ def gen_kernels():
 
 
 def run_sample(kind, kernel, n=160, sigma=0.13, deg=3, W=16, H=12, view=1, max_depth=64, srgb=True, extent=3.0,
-               seed=5, tag=''):
+               seed=5, tag='', hide_emitters=False, finite_maxt=False, unnormalised_quats=False):
     cloud = synthetic.make_cloud(n, sigma, seed=seed, sh_degree=deg)
+    if unnormalised_quats:      # quirk Q6: the maths never normalises (smoke.ply stores norms up to 1.0047)
+        cloud.data[::3, 6:10] *= 1.0047
+        cloud.data[1::5, 6:10] *= 0.996
     cam = synthetic.ring_camera(view, 8, W, H)
     o, d, mt = synthetic.camera_rays(cam)
     o, d, mt = o.astype(np.float64), d.astype(np.float64), mt.astype(np.float64)
     rng = np.random.default_rng(seed + 100)
+    if finite_maxt:             # every third ray stops inside the cloud (maxt applies to the re-based origin too)
+        mt[::3] = rng.uniform(0.6, 1.6, mt[::3].shape)
     data = torch.tensor(cloud.data.astype(np.float64), requires_grad=True)
     attrs = {}
     if kind == 'rf':
@@ -88,7 +93,7 @@ def run_sample(kind, kernel, n=160, sigma=0.13, deg=3, W=16, H=12, view=1, max_d
     else:
         sig = rng.uniform(0.002, 0.05, n)
         attrs['sigma_t'] = torch.tensor(sig[:, None], requires_grad=True)
-        props = R.Properties({'max_depth': max_depth, 'kernel_type': kernel})
+        props = R.Properties({'max_depth': max_depth, 'kernel_type': kernel, 'hide_emitters': hide_emitters})
         integ = tomo_mod.VolumetricPrimitiveTomographyIntegrator(props)
         attr_name = 'sigma_t'
     shape = R.RefShape(data, attrs, extent)
@@ -110,7 +115,7 @@ def run_sample(kind, kernel, n=160, sigma=0.13, deg=3, W=16, H=12, view=1, max_d
         integ.sample(dr.ADMode.Backward, scene, R._Sampler(), ray(), vec(dL), state, R.Bool(torch.ones(Rn, dtype=torch.bool)))
     out = {'data': cloud.data.astype(np.float64), 'attr': attrs[attr_name].detach().numpy()[:, 0], 'o': o, 'd': d,
            'maxt': mt, 'L': L_np, 'hits': hits, 'dL': dL, 'extent': extent, 'max_depth': max_depth, 'srgb': srgb,
-           'env': np.array(env), 'kernel': kernel,
+           'env': np.array(env), 'kernel': kernel, 'hide_emitters': hide_emitters,
            'g_data': data.grad.numpy() if data.grad is not None else np.zeros_like(cloud.data, dtype=np.float64),
            'g_attr': attrs[attr_name].grad.numpy()[:, 0] if attrs[attr_name].grad is not None else np.zeros(n)}
     if kind == 'rf':
@@ -131,3 +136,6 @@ if __name__ == '__main__':
     run_sample('tomo', 'gaussian', max_depth=-1)
     run_sample('tomo', 'epanechnikov', extent=1.0, max_depth=-1, tag='_extent1')
     run_sample('tomo', 'epanechnikov', extent=3.0, max_depth=7, tag='_extent3_depth7')
+    run_sample('tomo', 'gaussian', max_depth=-1, hide_emitters=True, finite_maxt=True, seed=8, tag='_hide_maxt')
+    run_sample('rf', 'gaussian', deg=2, unnormalised_quats=True, finite_maxt=True, seed=9, tag='_deg2_unnorm_maxt')
+    run_sample('rf', 'epanechnikov', deg=0, max_depth=3, seed=10, tag='_deg0_depth3')

@@ -37,7 +37,8 @@ def test_kernel_formulas_match_reference_source():
 
 
 SAMPLES = ["sample_rf_gaussian", "sample_rf_epanechnikov", "sample_rf_gaussian_deg1_depth5", "sample_tomo_gaussian",
-           "sample_tomo_epanechnikov_extent1", "sample_tomo_epanechnikov_extent3_depth7"]
+           "sample_tomo_epanechnikov_extent1", "sample_tomo_epanechnikov_extent3_depth7",
+           "sample_tomo_gaussian_hide_maxt", "sample_rf_gaussian_deg2_unnorm_maxt", "sample_rf_epanechnikov_deg0_depth3"]
 
 
 @pytest.mark.parametrize("name", SAMPLES)
@@ -47,7 +48,8 @@ def test_sample_loop_and_adjoint_match_reference_source(name):
     kernel = KID[str(z["kernel"])]
     sc = O.Scene(z["data"], z["attr"], z["sh"] if rf else None, float(z["extent"]), precision="f64", bvh=False)
     prm = O.Params(integrator=O.RF if rf else O.TOMO, kernel=kernel, max_depth=int(z["max_depth"]),
-                   srgb_primitives=bool(z["srgb"]), env=tuple(z["env"]), brute_force=True)
+                   srgb_primitives=bool(z["srgb"]), env=tuple(z["env"]), brute_force=True,
+                   hide_emitters=bool(z["hide_emitters"]) if "hide_emitters" in z.files else False)
     hits = z["hits"]
     cap = hits.shape[1]
     res = sc.forward(prm, z["o"], z["d"], z["maxt"], cap=cap)
