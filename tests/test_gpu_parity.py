@@ -268,8 +268,9 @@ GOLDEN_SAMPLES = ["sample_rf_gaussian", "sample_rf_epanechnikov", "sample_rf_gau
                   "sample_tomo_gaussian_hide_maxt", "sample_rf_gaussian_deg2_unnorm_maxt", "sample_rf_epanechnikov_deg0_depth3"]
 
 
+@pytest.mark.parametrize("tile", [False, True], ids=["per_ray", "tile"])
 @pytest.mark.parametrize("name", GOLDEN_SAMPLES)
-def test_cuda_path_against_reference_source_fixtures(name):
+def test_cuda_path_against_reference_source_fixtures(name, tile):
     """The CUDA path on the inputs of tests/golden/*.npz -- produced by EXECUTING the reference's own volprim_rf.py /
     volprim_tomography.py / common.py in float64 (tests/golden/make_golden.py) -- against the reference's outputs:
     ordered hit lists, radiance, and the PRB gradients.  fp32 vs fp64: a near-tie may swap two hits on a few rays, so
@@ -284,7 +285,7 @@ def test_cuda_path_against_reference_source_fixtures(name):
     acc.set_primitives(f32(z["data"]), f32(z["attr"]), f32(z["sh"]) if rf else None, float(z["extent"]))
     acc.build()
     p, _ = make_params(0 if rf else 1, kernel, max_depth=int(z["max_depth"]), srgb=bool(z["srgb"]), hide_emitters=hide,
-                       env=tuple(float(x) for x in z["env"]))
+                       env=tuple(float(x) for x in z["env"]), image=(16, 12) if tile else None)   # fixtures: 16x12 views
     hits = z["hits"]
     cap = hits.shape[1]
     o, d, mt = f32(z["o"]), f32(z["d"]), f32(np.minimum(z["maxt"], np.finfo(np.float32).max))
