@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VP_VERSION 100 /* 0.1.0 */
+#define VP_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define VP_API __attribute__((visibility("default")))
@@ -55,6 +55,11 @@ typedef struct vp_params {
     float env[3];            /* constant environment radiance    volprim_tomography.py:107   */
     int32_t image_width;     /* >0: rays are W x H pixel grids; threads walk them in 8x4 tiles */
     int32_t image_height;
+    int32_t use_rr;          /* Russian roulette active (rr_depth >= 0 and (rr_depth < max_depth or max_depth == -1),
+                                volprim_rf.py:39,177-183); primal pass only, like the reference                 */
+    uint32_t rr_depth;       /* `rr_depth`                                                                      */
+    uint32_t rr_seed;        /* seed of the `independent` sampler (PCG32 per ray, stream = TEA(seed, ray index)) */
+    uint32_t rr_skip;        /* 1-D samples every ray has drawn before sample() is entered (2 under mi.render)  */
 } vp_params;
 
 /* Perspective sensor, Mitsuba `perspective` plugin semantics (volprim/cameras.py:114-137). */
@@ -65,6 +70,38 @@ typedef struct vp_camera {
     float cx, cy;       /* principal_point_offset_{x,y}                                        */
     int32_t width, height;
 } vp_camera;
+
+/* Where the rays of a vp_render_* call come from: an explicit batch (the calling convention of
+ * scripts/radiosity/radiance_cache.py:252-266), or a perspective sensor whose rays are generated INSIDE the trace
+ * kernels (Sensor.sample_ray fused into the integrator launch: no ray buffers in HBM, 28 B per ray less traffic). */
+typedef struct vp_ray_source {
+    const float *ray_o;      /* device [R*3], or NULL when `camera` is set                                   */
+    const float *ray_d;      /* device [R*3], or NULL when `camera` is set                                   */
+    const float *ray_maxt;   /* device [R] or NULL (= infinity); unused with `camera` (far - near along the ray) */
+    const vp_camera *camera; /* HOST pointer or NULL.  Rays are pixel-major, then sample (like vp_raygen_perspective) */
+    const float *jitter;     /* device [R*2] sub-pixel offsets in [0,1) or NULL = pixel centres (camera only) */
+    int32_t spp;             /* samples per pixel (camera only)                                              */
+    int32_t row_begin;       /* first film row of this call; R = width * row_count * spp (camera only)        */
+    int32_t row_count;       /* 0 = all rows from row_begin to the bottom of the film                         */
+    int32_t reserved;
+} vp_ray_source;
+
+/* Ordered hit lists of a primal pass in compressed-row form (what the adjoint replays instead of walking the BVH a
+ * second time).  All arrays are caller-owned DEVICE memory.  Bytes kept per view: 4 per recorded hit + 8 per ray
+ * + 4 per primitive. */
+typedef struct vp_hit_record {
+    int64_t *ray_offsets;   /* [n_rays + 1]   list of ray r = ids[ray_offsets[r] .. ray_offsets[r + 1])            */
+    int32_t *ids;           /* [capacity]     primitive ids (numbering of vp_set_primitives), front to back        */
+    uint32_t *prim_offsets; /* [n_prims + 1]  exclusive prefix of the number of recorded hits per primitive        */
+    int64_t *total;         /* [2]            entries all lists need; rays whose list was cut at `id_cap`          */
+    int64_t capacity;       /* entries `ids` holds (< 2^32).  A record is usable iff total[0] <= capacity and
+                               total[1] == 0; vp_render_adjoint does nothing otherwise (the caller re-traces)     */
+    int32_t id_cap;         /* most hits recorded per ray (height of the transient dense scratch)                  */
+    int32_t reserved;
+} vp_hit_record;
+
+/* Reconstruction filters of the film (Mitsuba rfilter plugins `box`, `tent`, `gaussian`; volprim/cameras.py:117). */
+enum { VP_RFILTER_BOX = 0, VP_RFILTER_TENT = 1, VP_RFILTER_GAUSSIAN = 2 };
 
 /* Work counters of the last trace call (device-accumulated, read back on request). */
 typedef struct vp_stats {
@@ -105,7 +142,8 @@ VP_API int vp_refit(vp_ctx *ctx, void *stream);
  *   ray_o, ray_d [R*3]; ray_maxt [R] or NULL (= infinity)
  *   out_rgb [R*3]; out_T [R] final throughput beta (NULL ok); out_nhits [R] (NULL ok)
  *   out_hit_ids: NULL, or the ordered primitive-ID list of every ray, element (ray r, hit k) at
- *                out_hit_ids[r * id_ray_stride + k * id_hit_stride], k < id_cap, -1 padded. */
+ *                out_hit_ids[r * id_ray_stride + k * id_hit_stride], k < min(out_nhits[r], id_cap).  Entries beyond
+ *                a ray's hit count are NOT written (pre-fill the buffer if padding is wanted). */
 VP_API int vp_trace_forward(vp_ctx *ctx, const vp_params *params, int64_t n_rays, const float *ray_o, const float *ray_d,
                      const float *ray_maxt, float *out_rgb, float *out_T, uint32_t *out_nhits, int32_t *out_hit_ids,
                      int32_t id_cap, int64_t id_ray_stride, int64_t id_hit_stride, void *stream);
@@ -116,7 +154,9 @@ VP_API int vp_trace_forward(vp_ctx *ctx, const vp_params *params, int64_t n_rays
  * g_attr [N], g_sh [N*C] (NULL ok for tomography).
  * hit_ids: NULL -> the hit sequence is re-traced exactly like the primal; otherwise the lists a
  * previous vp_trace_forward recorded for the same rays (same strides), which are replayed without
- * touching the BVH (hit_counts [R] required then). */
+ * touching the BVH (hit_counts [R] required then; a ray with hit_counts[r] > id_cap replays only its first id_cap
+ * hits -- record with id_cap >= max_depth, or check the counts).
+ * Alignment: g_data10 8 bytes, g_sh 16 bytes when C % 4 == 0 (vector reductions); VP_E_INVALID otherwise. */
 VP_API int vp_trace_adjoint(vp_ctx *ctx, const vp_params *params, int64_t n_rays, const float *ray_o, const float *ray_d,
                      const float *ray_maxt, const float *d_L, const float *state_in, const int32_t *hit_ids,
                      const uint32_t *hit_counts, int32_t id_cap, int64_t id_ray_stride, int64_t id_hit_stride,
@@ -127,6 +167,53 @@ VP_API int vp_trace_adjoint(vp_ctx *ctx, const vp_params *params, int64_t n_rays
  * `jitter` NULL -> pixel centres; else [W*H*spp*2] sub-pixel offsets in [0,1). */
 VP_API int vp_raygen_perspective(vp_ctx *ctx, const vp_camera *cam, int32_t spp, const float *jitter, float *ray_o,
                           float *ray_d, float *ray_maxt, void *stream);
+
+/* ---- sensor-fused / record-replay entry points (what volprim_balance_b200.render() uses) ------------------------
+ * vp_render_forward: Integrator.sample(Primal) over `rays` (explicit batch, or rays generated in-kernel from a
+ * perspective sensor).  out_T / out_nhits may be NULL.  With `record` != NULL the ordered hit lists are kept in
+ * compressed-row form: the trace kernel writes them hit-major into a transient scratch of the context (bounded by
+ * splitting the call into row bands), a compaction pass copies them to record->ids at the exclusive-scan offsets of
+ * the hit counts, and the per-primitive hit counts are accumulated on the way (for the gather adjoint). */
+VP_API int vp_render_forward(vp_ctx *ctx, const vp_params *params, const vp_ray_source *rays, int64_t n_rays,
+                             float *out_rgb, float *out_T, uint32_t *out_nhits, const vp_hit_record *record,
+                             void *stream);
+
+/* vp_render_adjoint: Integrator.sample(Backward) replaying `record` (volprim_rf.py:106-165).  volprim_rf uses the
+ * GATHER formulation: a ray-major pass replays every list and writes 20 B of per-hit state into the bucket of the
+ * hit primitive, then one warp per primitive accumulates its bucket in registers and adds the 10 + 1 + C gradient
+ * floats to the caller's buffers exactly once -- no global reductions (the scatter formulation of vp_trace_adjoint
+ * saturates the L2 reduction units).  volprim_tomography replays with vector reductions like vp_trace_adjoint.
+ * Gradients are ADDED to g_data10 [N*10], g_attr [N], g_sh [N*C] (8-, 4- and 8-byte aligned); the buffers must not
+ * be written by anything else while the call runs.  Equivalent to vp_adjoint_begin + vp_adjoint_finish(0, N). */
+VP_API int vp_render_adjoint(vp_ctx *ctx, const vp_params *params, const vp_ray_source *rays, int64_t n_rays,
+                             const float *d_L, const float *state_in, const vp_hit_record *record, float *g_data10,
+                             float *g_attr, float *g_sh, void *stream);
+
+/* The two halves of vp_render_adjoint, so that a caller can overlap the gradient all-reduce of one primitive range
+ * with the accumulation of the next (examples/refine_3dg_dataset.py on several GPUs): vp_adjoint_begin runs the
+ * ray-major pass into the context's scratch; vp_adjoint_finish accumulates primitives [prim_begin, prim_end). */
+VP_API int vp_adjoint_begin(vp_ctx *ctx, const vp_params *params, const vp_ray_source *rays, int64_t n_rays,
+                            const float *d_L, const float *state_in, const vp_hit_record *record, float *g_data10,
+                            float *g_attr, float *g_sh, void *stream);
+VP_API int vp_adjoint_finish(vp_ctx *ctx, const vp_params *params, const vp_ray_source *rays, int64_t n_rays,
+                             const vp_hit_record *record, int64_t prim_begin, int64_t prim_end, float *g_data10,
+                             float *g_attr, float *g_sh, void *stream);
+
+/* Film (Mitsuba hdrfilm + reconstruction filter; batch film layout of examples/refine_3dg_dataset.py:96-107).
+ * Samples are pixel-major then sample, at pixel + jitter (NULL = centres).  vp_film_splat ADDS weight * radiance
+ * and the weights into accum [H*W*4] (caller-zeroed); vp_film_develop writes image [H*W*3] = rgb / weight;
+ * vp_film_adjoint gathers d_L [S*3] = sum over the pixels a sample touches of d_image * weight / pixel weight. */
+VP_API int vp_film_splat(int32_t width, int32_t height, int32_t spp, int32_t rfilter, const float *jitter,
+                         const float *radiance, float *accum, void *stream);
+VP_API int vp_film_develop(int32_t width, int32_t height, const float *accum, float *image, int64_t image_row_stride,
+                           void *stream);
+VP_API int vp_film_adjoint(int32_t width, int32_t height, int32_t spp, int32_t rfilter, const float *jitter,
+                           const float *accum, const float *d_image, int64_t d_image_row_stride, float *d_L,
+                           void *stream);
+
+/* Tunables of a context: "record_scratch_bytes" (transient dense hit-list scratch of vp_render_forward, default
+ * 1 GiB).  Returns VP_E_INVALID for an unknown name. */
+VP_API int vp_set_option(vp_ctx *ctx, const char *name, int64_t value);
 
 /* Copy the work counters of the most recent trace call to the host (synchronises `stream`). */
 VP_API int vp_get_stats(vp_ctx *ctx, vp_stats *host_out, void *stream);

@@ -35,6 +35,10 @@ class _Params(C.Structure):
         ("t_cutoff", C.c_double),
         ("eps_advance", C.c_double),
         ("env", C.c_double * 3),
+        ("use_rr", C.c_int32),
+        ("rr_depth", C.c_uint32),
+        ("rr_seed", C.c_uint32),
+        ("rr_skip", C.c_uint32),
     ]
 
 
@@ -50,12 +54,21 @@ class Params:
     t_cutoff: float = 0.01
     eps_advance: float = 1e-4
     env: tuple = (1.0, 1.0, 1.0)
+    rr_depth: int = -1            # volprim_rf.py:31; Russian roulette is active iff rr_depth >= 0 and
+    rr_seed: int = 0              # (rr_depth < max_depth or max_depth == -1)            volprim_rf.py:39
+    rr_skip: int = 0
+
+    @property
+    def use_rr(self) -> bool:
+        return self.rr_depth >= 0 and (self.rr_depth < self.max_depth or self.max_depth == -1)
 
     def to_c(self) -> _Params:
         md = 0xFFFFFFFF if self.max_depth == -1 else int(self.max_depth)
+        rrd = 0xFFFFFFFF if self.rr_depth == -1 else int(self.rr_depth)
         return _Params(int(self.integrator), int(self.kernel), md, int(self.srgb_primitives),
                        int(self.hide_emitters), int(self.brute_force), int(self.diagnostics), 0,
-                       float(self.t_cutoff), float(self.eps_advance), (C.c_double * 3)(*self.env))
+                       float(self.t_cutoff), float(self.eps_advance), (C.c_double * 3)(*self.env),
+                       int(self.use_rr), rrd, int(self.rr_seed) & 0xFFFFFFFF, int(self.rr_skip) & 0xFFFFFFFF)
 
 
 def build(force: bool = False) -> None:
@@ -85,6 +98,9 @@ def _lib(precision: str):
                                           C.c_int32, C.POINTER(C.c_double)]
         lib.orc_trace_adjoint.argtypes = [C.c_void_p, C.POINTER(_Params), C.c_int64, rp, rp, rp, rp, rp,
                                           C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        lib.orc_replay_forward.argtypes = [C.c_void_p, C.POINTER(_Params), C.c_int64, rp, rp, rp, C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_uint32), C.c_int32, rp, rp, C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_double), C.POINTER(C.c_double)]
         lib.orc_quat_to_matrix.argtypes = [rp, rp]
         lib.orc_sh_eval.argtypes = [rp, C.c_int, rp]
         lib.orc_srgb_to_linear.restype = real
@@ -99,6 +115,10 @@ def _lib(precision: str):
         lib.orc_density_integral.argtypes = [C.c_int, rp, rp, rp, real]
         lib.orc_rf_transmission.restype = real
         lib.orc_rf_transmission.argtypes = [C.c_int, rp, rp, rp, real]
+        lib.orc_pcg32_float_at.restype = C.c_float
+        lib.orc_pcg32_float_at.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+        lib.orc_pcg32_uint_at.restype = C.c_uint32
+        lib.orc_pcg32_uint_at.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
         lib.orc_num_threads.restype = C.c_int
         lib.orc_set_num_threads.argtypes = [C.c_int]
         _LIBS[precision] = (lib, real, np.float32 if precision == "f32" else np.float64)
@@ -169,6 +189,25 @@ class Scene:
                                    _ptr(ids, C.c_int32), _ptr(ht, C.c_double), cap, _ptr(fr, C.c_double))
         return ForwardResult(rgb, beta, nh, ids, ht, fr)
 
+    def replay(self, params: Params, o, d, maxt, ids, counts):
+        """Evaluate GIVEN hit lists (ids [R, cap], counts [R]) with the loop's arithmetic.  Returns a dict:
+        rgb, beta, valid (every listed primitive was a legal hit), hit_beta [R, cap], cmax [R]."""
+        o, d, m = self._rays(o, d, maxt)
+        R = o.shape[0]
+        ids = np.ascontiguousarray(np.asarray(ids, np.int32).reshape(R, -1))
+        cap = ids.shape[1]
+        counts = np.ascontiguousarray(np.asarray(counts, np.uint32).reshape(R))
+        rgb = np.zeros((R, 3), self.np_real)
+        beta = np.zeros(R, self.np_real)
+        valid = np.zeros(R, np.int32)
+        hb = np.ones((R, max(cap, 1)), np.float64)
+        cm = np.zeros(R, np.float64)
+        p = params.to_c()
+        self.lib.orc_replay_forward(self._h, C.byref(p), R, _ptr(o, self.real), _ptr(d, self.real), _ptr(m, self.real),
+                                    _ptr(ids, C.c_int32), _ptr(counts, C.c_uint32), cap, _ptr(rgb, self.real),
+                                    _ptr(beta, self.real), _ptr(valid, C.c_int32), _ptr(hb, C.c_double), _ptr(cm, C.c_double))
+        return {"rgb": rgb, "beta": beta, "valid": valid.astype(bool), "hit_beta": hb, "cmax": cm}
+
     def adjoint(self, params: Params, o, d, dL, state_in, maxt=None):
         """Returns (g_data [N,10], g_attr [N], g_sh [N,C]) in float64."""
         o, d, m = self._rays(o, d, maxt)
@@ -238,6 +277,14 @@ def rf_transmission(kernel, o, d, rec10, opacity, precision="f32"):
     lib, real, npr = _lib(precision)
     return lib.orc_rf_transmission(int(kernel), _ptr(_vec(o, npr, 3), real), _ptr(_vec(d, npr, 3), real),
                                    _ptr(_vec(rec10, npr, 10), real), real(opacity))
+
+
+def pcg32_float_at(seed: int, idx: int, n: int) -> float:
+    return float(_lib("f32")[0].orc_pcg32_float_at(seed & 0xFFFFFFFF, idx & 0xFFFFFFFF, n & 0xFFFFFFFF))
+
+
+def pcg32_uint_at(initstate: int, initseq: int, n: int) -> int:
+    return int(_lib("f32")[0].orc_pcg32_uint_at(initstate, initseq, n))
 
 
 def num_threads() -> int:

@@ -78,6 +78,10 @@ typedef struct {
     double t_cutoff;         /* 0.01                           volprim_rf.py:173-174 */
     double eps_advance;      /* 1e-4                           volprim_rf.py:149 */
     double env[3];           /* constant environment radiance  volprim_tomography.py:107 */
+    int32_t use_rr;          /* Russian roulette active        volprim_rf.py:39 */
+    uint32_t rr_depth;       /*                                volprim_rf.py:31-36 */
+    uint32_t rr_seed;        /* seed of the `independent` sampler */
+    uint32_t rr_skip;        /* 1-D samples drawn per ray before sample() (2 under mi.render: the film position) */
 } orc_params;
 
 typedef struct {
@@ -583,6 +587,41 @@ typedef struct {
     int le_finite[3];
 } rf_hit;
 
+/*
+ * `sampler.next_1d()` of Mitsuba's `independent` sampler (THIRD-PARTY, PARITY UNPINNED; published algorithms):
+ * one PCG32 stream per wavefront lane, seeded as PCG32(initstate = v0, initseq = v1) with (v0, v1) =
+ * sample_tea_32(seed, lane index) (4 rounds of the Tiny Encryption Algorithm), next_float32 =
+ * bits((next_uint32 >> 9) | 0x3f800000) - 1.  Returns the n-th float (n = 0 first) of lane `idx`.
+ */
+static uint32_t pcg32_uint_at(uint64_t initstate, uint64_t initseq, uint32_t n)
+{
+    const uint64_t mult = 0x5851f42d4c957f2dull;
+    uint64_t inc = (initseq << 1) | 1u, state = 0;
+    state = state * mult + inc;
+    state += initstate;
+    state = state * mult + inc;
+    for (uint32_t i = 0; i < n; ++i) state = state * mult + inc;
+    uint32_t xorshifted = (uint32_t)(((state >> 18u) ^ state) >> 27u);
+    uint32_t rot = (uint32_t)(state >> 59u);
+    return (xorshifted >> rot) | (xorshifted << ((0u - rot) & 31u));
+}
+
+static float pcg32_float_at(uint32_t seed, uint32_t idx, uint32_t n)
+{
+    uint32_t v0 = seed, v1 = idx, sum = 0;
+    for (int i = 0; i < 4; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    union { uint32_t u; float f; } cv;
+    cv.u = (pcg32_uint_at((uint64_t)v0, (uint64_t)v1, n) >> 9) | 0x3f800000u;
+    return cv.f - 1.0f;
+}
+
+EXPORT uint32_t orc_pcg32_uint_at(uint64_t initstate, uint64_t initseq, uint32_t n) { return pcg32_uint_at(initstate, initseq, n); }
+EXPORT float orc_pcg32_float_at(uint32_t seed, uint32_t idx, uint32_t n) { return pcg32_float_at(seed, idx, n); }
+
 static void rf_interact(const orc_scene *sc, const orc_params *pr, int64_t j, const REAL o[3], const REAL d[3],
                         const REAL *Y, REAL beta, rf_hit *r)
 {
@@ -667,6 +706,16 @@ EXPORT void orc_trace_forward(const orc_scene *sc, const orc_params *pr, int64_t
             }
             depth += 1;                                                  /* rf:170 */
             if (pr->integrator == ORC_RF && !(beta > (REAL)pr->t_cutoff)) active = 0; /* rf:173-174 */
+            /* Russian roulette, primal pass only (rf:177-183).  The sampler advances once per loop iteration, so
+             * this iteration's sample is number rr_skip + depth - 1 of the ray's stream. */
+            if (pr->integrator == ORC_RF && pr->use_rr && active) {
+                REAL rr_prob = beta > R_(0.1) ? beta : R_(0.1);
+                if (depth >= pr->rr_depth && beta < R_(0.1)) {
+                    beta = beta * (R_(1) / rr_prob);
+                    float u = pcg32_float_at(pr->rr_seed, (uint32_t)r, pr->rr_skip + depth - 1u);
+                    if (!((REAL)u < rr_prob)) active = 0;
+                }
+            }
             if (!(depth < pr->max_depth)) active = 0;                    /* rf:186 / tomo:125 */
         }
         if (pr->integrator == ORC_RF && pr->srgb_primitives)
@@ -900,6 +949,69 @@ EXPORT REAL orc_rf_transmission(int kernel, const REAL o[3], const REAL d[3], co
     make_ellipsoid(rec10, R_(3), &e);
     return rf_transmission(o, d, &e, opacity, kernel, NULL, NULL);
 }
+/*
+ * Replay of GIVEN hit lists with the loop's own arithmetic (test helper for rays whose list is fragile: near-tied
+ * entries, entries at the epsilon cull).  For every ray the listed primitives are taken in order as the hits of
+ * volprim_rf.py:120-186 / volprim_tomography.py:67-125: the entry distance comes from ray_ellipsoid at the current
+ * re-based origin, the interaction and the origin advance are the forward loop's.  Outputs: rgb [R*3], beta [R],
+ * valid [R] (1 iff every listed primitive was a front-face hit with 0 < t <= maxt), hit_beta [R*cap] (throughput
+ * BEFORE hit k), cmax [R] (largest colour channel met; 1 for tomography).
+ */
+EXPORT void orc_replay_forward(const orc_scene *sc, const orc_params *pr, int64_t R, const REAL *ray_o, const REAL *ray_d,
+                               const REAL *ray_maxt, const int32_t *ids, const uint32_t *counts, int32_t cap, REAL *rgb,
+                               REAL *beta_out, int32_t *valid, double *hit_beta, double *cmax)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t r = 0; r < R; ++r) {
+        REAL o[3] = { ray_o[3 * r], ray_o[3 * r + 1], ray_o[3 * r + 2] };
+        REAL d[3] = { ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2] };
+        REAL maxt = ray_maxt ? ray_maxt[r] : REAL_MAX;
+        REAL Y[16];
+        if (pr->integrator == ORC_RF && sc->sh_floats) sh_eval(d, sc->sh_degree, Y);
+        REAL beta = R_(1), L[3] = { R_(0), R_(0), R_(0) };
+        int ok = 1, escaped = 1;
+        double cm = pr->integrator == ORC_RF ? 0.0 : 1.0;
+        uint32_t n = counts[r] < (uint32_t)cap ? counts[r] : (uint32_t)cap;
+        uint32_t depth = 0;
+        for (uint32_t k = 0; k < n; ++k) {
+            int64_t j = ids[r * cap + k];
+            if (j < 0 || j >= sc->n) { ok = 0; break; }
+            ellipsoid e;
+            gather(sc, j, &e);
+            REAL tn, tf;
+            if (!ray_ellipsoid(o, d, &e, &tn, &tf, NULL) || !(tn > R_(0)) || !(tn <= maxt)) { ok = 0; break; }
+            if (hit_beta) hit_beta[r * cap + k] = (double)beta;
+            if (pr->integrator == ORC_RF) {
+                rf_hit q;
+                rf_interact(sc, pr, j, o, d, Y, beta, &q);
+                for (int ch = 0; ch < 3; ++ch) {
+                    L[ch] = L[ch] + q.Le[ch];
+                    if ((double)q.col[ch] > cm) cm = (double)q.col[ch];
+                }
+                beta = beta * q.T;
+            } else {
+                beta = beta * tomo_interact(sc, pr, j, o, d, NULL, NULL);
+            }
+            for (int a = 0; a < 3; ++a) {
+                REAL p = FMA(d[a], tn, o[a]);
+                o[a] = FMA(d[a], (REAL)pr->eps_advance, p);
+            }
+            depth += 1;
+            if (pr->integrator == ORC_RF && !(beta > (REAL)pr->t_cutoff)) { escaped = 0; }
+            if (!(depth < pr->max_depth)) { escaped = 0; }
+        }
+        /* tomography adds the environment when the ray leaves the cloud (a list that ended by max_depth does not) */
+        if (pr->integrator == ORC_TOMO && escaped && !(depth == 0 && pr->hide_emitters))
+            for (int ch = 0; ch < 3; ++ch) L[ch] += beta * (REAL)pr->env[ch];
+        if (pr->integrator == ORC_RF && pr->srgb_primitives)
+            for (int ch = 0; ch < 3; ++ch) L[ch] = srgb_to_linear(L[ch]);
+        for (int ch = 0; ch < 3; ++ch) rgb[3 * r + ch] = L[ch];
+        if (beta_out) beta_out[r] = beta;
+        if (valid) valid[r] = ok;
+        if (cmax) cmax[r] = cm;
+    }
+}
+
 EXPORT int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -22,15 +22,23 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "volprim_cuda.h")).read()
     declared = set(re.findall(r"VP_API[^;(]*?\b(vp_[a-z_]+)\s*\(", hdr))
-    assert len(declared) >= 12
+    assert len(declared) >= 21
     assert declared == set(_cabi.SIGNATURES), "ctypes table and header disagree"
     lib = _cabi.load_library()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.vp_version() == 100
+    assert lib.vp_version() == 200
     # struct layouts must match the header (sizes are part of the ABI)
-    assert ctypes.sizeof(_cabi.vp_params) == 48 and ctypes.sizeof(_cabi.vp_camera) == 76
-    assert ctypes.sizeof(_cabi.vp_stats) == 56
+    assert ctypes.sizeof(_cabi.vp_params) == 64 and ctypes.sizeof(_cabi.vp_camera) == 76
+    assert ctypes.sizeof(_cabi.vp_stats) == 56 and ctypes.sizeof(_cabi.vp_ray_source) == 56
+    assert ctypes.sizeof(_cabi.vp_hit_record) == 48
+    # the structs of the header and of the ctypes mirror list the same fields in the same order
+    for name, cls in (("vp_params", _cabi.vp_params), ("vp_camera", _cabi.vp_camera), ("vp_ray_source", _cabi.vp_ray_source),
+                      ("vp_hit_record", _cabi.vp_hit_record), ("vp_stats", _cabi.vp_stats)):
+        body = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + ";", hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = re.findall(r"\b\*?\s*([a-z_0-9]+)(?:\[\d+\])?\s*[;,]", body)
+        assert fields == [f[0] for f in cls._fields_], (name, fields)
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -57,9 +65,10 @@ def test_integrator_parameters_defaults_and_errors():
         RF({"rr_depth": -3})
     with pytest.raises(Exception, match="Unknown kernel type"):
         Tomo({"kernel_type": "triangle"})
-    with pytest.raises(NotImplementedError):      # RR would need Mitsuba's sampler stream
-        RF({"max_depth": 64, "rr_depth": 5})
-    RF({"max_depth": 64, "rr_depth": 64})         # what every reference example passes
+    assert RF({"max_depth": 64, "rr_depth": 5}).use_rr and RF({"max_depth": -1, "rr_depth": 0}).use_rr   # volprim_rf.py:39
+    assert not RF({"max_depth": 64, "rr_depth": 64}).use_rr      # what every reference example passes
+    pr = RF({"max_depth": 64, "rr_depth": 5, "rr_seed": 9, "rr_skip": 2})._vp_params(None)
+    assert (pr.use_rr, pr.rr_depth, pr.rr_seed, pr.rr_skip) == (1, 5, 9, 2) and RF()._vp_params(None).use_rr == 0
     seen = {}
     rf.traverse(type("CB", (), {"put_parameter": lambda self, k, v, f: seen.__setitem__(k, v)})())
     assert set(seen) == {"max_depth", "rr_depth", "srgb_primitives", "kernel_type", "hide_emitters"}

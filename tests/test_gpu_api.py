@@ -8,7 +8,8 @@ import torch
 import volprim_balance_b200 as vp
 from oracle import oracle as O
 from volprim_balance_b200 import synthetic
-from tests.parity_utils import RGB_ATOL, RGB_RTOL, compare_forward, gpu_scene, grad_close, make_params, oracle_scene
+from tests.parity_utils import (RGB_ATOL, RGB_RTOL, compare_forward, gpu_scene, grad_close, make_params, oracle_scene,
+                                robust_mask)
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -74,7 +75,10 @@ def test_render_autograd_matches_oracle_adjoint_reference_exact_and_corrected():
     keys = ["primitives.data", "primitives.opacities", "primitives.sh_coeffs"]
     o, d, mt = synthetic.camera_rays(cam)
     osc = oracle_scene(cloud)
-    w = torch.from_numpy(np.random.default_rng(2).normal(size=(32, 48, 3)).astype(np.float32)).cuda()
+    w_np = np.random.default_rng(2).normal(size=(32 * 48, 3)).astype(np.float32)
+    # gradients are compared elementwise at 1e-3: rays whose list may legally differ in fp32 carry no weight
+    w_np[~robust_mask(osc.forward(O.Params(integrator=O.RF, kernel=O.GAUSS, max_depth=64), o, d, mt, cap=64, fragility=True))] = 0
+    w = torch.from_numpy(w_np.reshape(32, 48, 3)).cuda()
     for mode in ("reference_exact", "corrected"):
         for k in keys:
             params[k].requires_grad_(True)
@@ -90,9 +94,9 @@ def test_render_autograd_matches_oracle_adjoint_reference_exact_and_corrected():
         else:                           # true gradient: chain through srgb_to_linear, state_in in sRGB space
             deriv = O.srgb_to_linear_deriv(ref.rgb)
             rd, ra, rs = osc.adjoint(op, o, d, dL * deriv, ref.rgb, mt)
-        grad_close(params[keys[0]].grad.cpu().numpy(), rd, rtol=5e-3, what=f"{mode} d data")
-        grad_close(params[keys[1]].grad.cpu().numpy(), ra, rtol=5e-3, what=f"{mode} d opacities")
-        grad_close(params[keys[2]].grad.cpu().numpy(), rs, rtol=5e-3, what=f"{mode} d sh")
+        grad_close(params[keys[0]].grad.cpu().numpy(), rd, what=f"{mode} d data")
+        grad_close(params[keys[1]].grad.cpu().numpy(), ra, what=f"{mode} d opacities")
+        grad_close(params[keys[2]].grad.cpu().numpy(), rs, what=f"{mode} d sh")
 
 
 def test_params_update_rebuild_and_refit_agree():
@@ -224,16 +228,18 @@ def test_batch_sensor_tent_filter_and_tomography_autograd():
         params[k].requires_grad_(True)
     s0 = vp.load_dict(_sensor_dict(cams[1], "box"))
     im = vp.render(scene, params, sensor=s0, spp=1, jitter=False)
-    w = torch.from_numpy(np.random.default_rng(5).normal(size=(24, 40, 3)).astype(np.float32)).cuda()
-    (im * w).sum().backward()
     o, d, mt = synthetic.camera_rays(cams[1])
     osc = O.Scene(cloud.data, sig, None, 3.0)
     op = O.Params(integrator=O.TOMO, kernel=O.GAUSS, max_depth=-1, env=(0.8, 0.8, 0.8))
-    ref = osc.forward(op, o, d, mt)
+    ref = osc.forward(op, o, d, mt, cap=256, fragility=True)
+    w_np = np.random.default_rng(5).normal(size=(24 * 40, 3)).astype(np.float32)
+    w_np[~robust_mask(ref)] = 0
+    w = torch.from_numpy(w_np.reshape(24, 40, 3)).cuda()
+    (im * w).sum().backward()
     np.testing.assert_allclose(im.detach().reshape(-1, 3).cpu().numpy(), ref.rgb, atol=2e-4, rtol=2e-3)
     rd, ra, _ = osc.adjoint(op, o, d, w.reshape(-1, 3).cpu().numpy(), ref.rgb, mt)
-    grad_close(params["primitives.data"].grad.cpu().numpy(), rd, rtol=5e-3, what="tomography d data")
-    grad_close(params["primitives.sigma_t"].grad.cpu().numpy(), ra, rtol=5e-3, what="tomography d sigma_t")
+    grad_close(params["primitives.data"].grad.cpu().numpy(), rd, what="tomography d data")
+    grad_close(params["primitives.sigma_t"].grad.cpu().numpy(), ra, what="tomography d sigma_t")
 
 
 def test_explicit_ray_batches_nonunit_directions_and_finite_maxt():

@@ -30,10 +30,11 @@ def test_rf_forward_matches_oracle(kernel, deg, tile):
     p, op = make_params(0, kernel, max_depth=128, image=(64, 48) if tile else None)
     acc = gpu_scene(cloud)
     res = acc.trace_forward(p, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt), record_cap=128)
-    ref = oracle_scene(cloud).forward(op, o, d, mt, cap=128, fragility=True)
-    st = compare_forward(res, ref, 128)
+    osc = oracle_scene(cloud)
+    ref = osc.forward(op, o, d, mt, cap=128, fragility=True)
+    st = compare_forward(res, ref, 128, replay=(osc, op, o, d, mt))
     assert st["mean_hits"] > 5
-    print(st, acc.stats())
+    print({k: v for k, v in st.items() if k[0] != "_"}, acc.stats())
 
 
 @pytest.mark.parametrize("tile", [False, True], ids=["per_ray", "tile"])
@@ -46,10 +47,11 @@ def test_tomography_forward_matches_oracle(kernel, tile):
     p, op = make_params(1, kernel, max_depth=-1, env=(1.0, 0.5, 0.25), image=(64, 48) if tile else None)
     acc = gpu_scene(cloud, attr=sig, sh=False)
     res = acc.trace_forward(p, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(mt), record_cap=256)
-    ref = oracle_scene(cloud, attr=sig, sh=False).forward(op, o, d, mt, cap=256, fragility=True)
-    st = compare_forward(res, ref, 256)
+    osc = oracle_scene(cloud, attr=sig, sh=False)
+    ref = osc.forward(op, o, d, mt, cap=256, fragility=True)
+    st = compare_forward(res, ref, 256, replay=(osc, op, o, d, mt), srgb=False)
     assert ref.beta.min() < 0.99
-    print(st)
+    print({k: v for k, v in st.items() if k[0] != "_"})
 
 
 @pytest.mark.parametrize("kernel,replay,tile", [(0, True, False), (0, False, False), (1, True, True), (0, False, True)])
@@ -297,9 +299,20 @@ def test_cuda_path_against_reference_source_fixtures(name, tile):
     rgb = res.rgb.cpu().numpy()
     ok = np.abs(rgb - z["L"]) <= RGB_ATOL + RGB_RTOL * np.abs(z["L"])
     assert ok[same].all(), f"radiance: max abs diff {np.abs(rgb - z['L'])[same].max()}"
-    g_data, g_attr, g_sh = acc.trace_adjoint(p, o, d, mt, f32(z["dL"]), f32(z["L"]))
-    tol = 2e-3 if same.all() else 2e-2          # a swapped pair of near-tied hits perturbs that ray's gradient
-    e1 = grad_close(g_data.cpu().numpy().reshape(-1, 10), z["g_data"], rtol=tol, what=name + " d data")
-    e2 = grad_close(g_attr.cpu().numpy(), z["g_attr"], rtol=tol, what=name + " d attr")
-    e3 = grad_close(g_sh.cpu().numpy().reshape(z["g_sh"].shape), z["g_sh"], rtol=tol, what=name + " d sh") if rf else 0.0
+    # Gradients, elementwise at the contract's tolerance.  If fp32 swapped a near-tie on some rays, those rays are taken
+    # out on BOTH sides: the float64 oracle (pinned to these fixtures with all rays by tests/test_oracle_golden.py)
+    # supplies the gradient of the remaining rays.
+    dL = np.array(z["dL"], np.float64)
+    want = (z["g_data"], z["g_attr"], z["g_sh"] if rf else None)
+    if not same.all():
+        dL[~same] = 0
+        from oracle import oracle as O
+        osc = O.Scene(z["data"], z["attr"], z["sh"] if rf else None, float(z["extent"]), precision="f64")
+        op = O.Params(integrator=O.RF if rf else O.TOMO, kernel=kernel, max_depth=int(z["max_depth"]), srgb_primitives=bool(z["srgb"]),
+                      hide_emitters=hide, env=tuple(float(x) for x in z["env"]))
+        want = osc.adjoint(op, z["o"], z["d"], dL, z["L"], np.minimum(z["maxt"], np.finfo(np.float32).max))
+    g_data, g_attr, g_sh = acc.trace_adjoint(p, o, d, mt, f32(dL), f32(z["L"]))
+    e1 = grad_close(g_data.cpu().numpy().reshape(-1, 10), np.asarray(want[0]).reshape(-1, 10), what=name + " d data")
+    e2 = grad_close(g_attr.cpu().numpy(), want[1], what=name + " d attr")
+    e3 = grad_close(g_sh.cpu().numpy().reshape(np.asarray(want[2]).shape), want[2], what=name + " d sh") if rf else 0.0
     print(name, "identical lists", same.mean(), "grad errors", e1, e2, e3)

@@ -126,3 +126,39 @@ def test_sh_basis_matches_3dgs_constants():
            C3[2] * y * (4 * z * z - x * x - y * y), C3[3] * z * (2 * z * z - 3 * x * x - 3 * y * y),
            C3[4] * x * (4 * z * z - x * x - y * y), C3[5] * z * (x * x - y * y), C3[6] * x * (x * x - 3 * y * y)]
     np.testing.assert_allclose(Y, ref, rtol=1e-12, atol=1e-14)
+
+
+def test_pcg32_matches_the_published_known_answer_vector():
+    """PCG32 (pcg-c-basic demo, pcg32_srandom(42, 54)): the generator behind the Russian-roulette restatement."""
+    want = [0xa15c02b7, 0x7b47f409, 0xba1d3330, 0x83d2f293, 0xbfa4784b, 0xcbed606e]
+    assert [O.pcg32_uint_at(42, 54, k) for k in range(6)] == want
+    u = [O.pcg32_float_at(3, 7, k) for k in range(64)]
+    assert all(0.0 <= x < 1.0 for x in u) and len(set(u)) == 64
+    assert O.pcg32_float_at(3, 7, 5) != O.pcg32_float_at(3, 8, 5) != O.pcg32_float_at(4, 7, 5)
+
+
+def test_russian_roulette_and_replay_of_the_oracle():
+    """volprim_rf.py:177-183: with rr_depth < max_depth, rays with beta in (0.01, 0.1) survive with probability 0.1
+    and are rescaled by 10; unbiased.  orc_replay_forward re-evaluates the loop's own hit lists bit for bit."""
+    from volprim_balance_b200 import synthetic
+    n = 4000
+    cloud = synthetic.make_cloud(n, synthetic.sigma0_for_hits(n, 40), seed=2, sh_degree=1)
+    o, d, mt = synthetic.camera_rays(synthetic.ring_camera(0, 8, 48, 32))
+    sc = O.Scene(cloud.data, cloud.opacities, cloud.sh_coeffs, 3.0)
+    off = O.Params(integrator=O.RF, max_depth=64)
+    assert not off.use_rr and not O.Params(max_depth=64, rr_depth=64).use_rr and O.Params(max_depth=-1, rr_depth=0).use_rr
+    a = sc.forward(off, o, d, mt, cap=64)
+    rp = sc.replay(off, o, d, mt, a.hit_ids, a.nhits)
+    assert rp["valid"].all() and np.array_equal(rp["rgb"], a.rgb) and np.array_equal(rp["beta"], a.beta)
+    assert (rp["hit_beta"][:, 0] == 1).all() and (np.diff(rp["hit_beta"], axis=1)[a.hit_ids[:, 1:] >= 0] <= 0).all()
+    means = []
+    for seed in range(8):
+        b = sc.forward(O.Params(integrator=O.RF, max_depth=64, rr_depth=2, rr_seed=seed), o, d, mt, cap=64)
+        assert (b.nhits < a.nhits).mean() > 0.2          # most rays that reach beta < 0.1 are ended there
+        means.append(b.rgb.mean())
+    assert abs(np.mean(means) - a.rgb.mean()) < 0.01
+    # a list with a primitive the ray never enters is reported invalid
+    bad = a.hit_ids.copy()
+    far = int(np.argmax(np.linalg.norm(cloud.data[:, :3] - (o[0] + d[0] * 4), axis=1)))
+    bad[0, 0] = far
+    assert not sc.replay(off, o, d, mt, bad, a.nhits)["valid"][0]

@@ -23,6 +23,25 @@ def test_shards_partition_views_and_rows():
         assert all(b[0] % 4 == 0 for b in bands if b[1] > b[0])
 
 
+def test_packed_gradient_segments_are_aligned_and_ranges_tile():
+    for n in (11, 12, 1001):
+        g = {"data": torch.arange(n * 10.0), "opacities": torch.arange(n * 1.0), "sh_coeffs": torch.arange(n * 27.0)}
+        keys = sorted(g)
+        flat = parallel.pack_gradients(g, keys)
+        back = parallel.unpack_gradients(flat, g, keys)
+        assert all(torch.equal(back[k], g[k]) for k in g)
+        assert all((back[k].data_ptr() - flat.data_ptr()) % 16 == 0 for k in g)      # any N, aligned slices
+        b = parallel.GradientBucket(n, 27, "cpu")
+        assert all((t.data_ptr() - b.flat.data_ptr()) % 16 == 0 for t in b.tensors())
+        assert b.data.numel() == n * 10 and b.attr.numel() == n and b.sh.numel() == n * 27
+        for chunks in (1, 3, 4, 64):
+            r = parallel.chunk_ranges(n, chunks)
+            assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == c[0] for a, c in zip(r, r[1:]))
+            assert all(p0 % 4 == 0 for p0, _ in r)
+            views = [b.chunk_views(p0, p1) for p0, p1 in r]
+            assert sum(v[0].numel() for v in views) == n * 10 and sum(v[2].numel() for v in views) == n * 27
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -41,6 +60,22 @@ def _worker(rank, ws, port, q):
         red = parallel.allreduce_gradients(g)
         ok = bool((red["data"] == 3).all() and torch.equal(red["opacities"], torch.arange(n, dtype=torch.float32) * 3)
                   and (red["sh_coeffs"] == 11).all())
+        b = parallel.GradientBucket(n, C, "cpu")
+        b.data += rank + 1
+        b.sh += 10 ** rank
+        for p0, p1 in parallel.chunk_ranges(n, 3):
+            for w in b.all_reduce_chunk(p0, p1):
+                w.wait()
+        ok = ok and bool((b.data == 3).all() and (b.sh == 11).all() and (b.attr == 0).all())
+
+        class _S:   # image-tile sharding: every rank renders its row band, rank 0 assembles
+            width, height = 6, 10
+        band_of = lambda scene, sensor, rows: torch.arange(rows[0], rows[1], dtype=torch.float32)[:, None, None].expand(-1, 6, 3)
+        tiled = parallel.render_tiles(None, _S, band_of)
+        if rank == 0:
+            ok = ok and tiled.shape == (10, 6, 3) and torch.equal(tiled[:, 0, 0], torch.arange(10.0))
+        else:
+            ok = ok and tiled is None
         n_views = 5
         local = {v: torch.full((4, 6, 3), float(v)) for v in parallel.shard_views(n_views)}
         imgs = parallel.gather_images(local, n_views, dst=0)

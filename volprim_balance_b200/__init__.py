@@ -17,6 +17,6 @@ from .integrators import ADMode, Ellipsoid, EllipsoidsFactory, Properties, Ray3f
 from . import scene as _scene
 from .scene import (BatchSensor, EllipsoidsShape, PerspectiveSensor, Scene, SceneParameters, load_dict, render,
                     render_to_host, traverse)
-from . import cameras, io, optimizers, utils, synthetic
+from . import cameras, io, optimizers, parallel, training, utils, synthetic
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -34,6 +34,10 @@ class vp_params(C.Structure):
         ("env", C.c_float * 3),
         ("image_width", C.c_int32),
         ("image_height", C.c_int32),
+        ("use_rr", C.c_int32),
+        ("rr_depth", C.c_uint32),
+        ("rr_seed", C.c_uint32),
+        ("rr_skip", C.c_uint32),
     ]
 
 
@@ -48,6 +52,36 @@ class vp_camera(C.Structure):
         ("width", C.c_int32),
         ("height", C.c_int32),
     ]
+
+
+class vp_ray_source(C.Structure):
+    _fields_ = [
+        ("ray_o", C.c_void_p),
+        ("ray_d", C.c_void_p),
+        ("ray_maxt", C.c_void_p),
+        ("camera", C.POINTER(vp_camera)),
+        ("jitter", C.c_void_p),
+        ("spp", C.c_int32),
+        ("row_begin", C.c_int32),
+        ("row_count", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class vp_hit_record(C.Structure):
+    _fields_ = [
+        ("ray_offsets", C.c_void_p),
+        ("ids", C.c_void_p),
+        ("prim_offsets", C.c_void_p),
+        ("total", C.c_void_p),
+        ("capacity", C.c_int64),
+        ("id_cap", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+RFILTER_BOX, RFILTER_TENT, RFILTER_GAUSSIAN = 0, 1, 2
+RFILTERS = {"box": RFILTER_BOX, "tent": RFILTER_TENT, "gaussian": RFILTER_GAUSSIAN}
 
 
 class vp_stats(C.Structure):
@@ -77,6 +111,18 @@ SIGNATURES = {
     "vp_trace_adjoint": (C.c_int, [_VP, C.POINTER(vp_params), C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
                                    C.c_int32, C.c_int64, C.c_int64, _VP, _VP, _VP, _VP]),
     "vp_raygen_perspective": (C.c_int, [_VP, C.POINTER(vp_camera), C.c_int32, _VP, _VP, _VP, _VP, _VP]),
+    "vp_render_forward": (C.c_int, [_VP, C.POINTER(vp_params), C.POINTER(vp_ray_source), C.c_int64, _VP, _VP, _VP,
+                                    C.POINTER(vp_hit_record), _VP]),
+    "vp_render_adjoint": (C.c_int, [_VP, C.POINTER(vp_params), C.POINTER(vp_ray_source), C.c_int64, _VP, _VP,
+                                    C.POINTER(vp_hit_record), _VP, _VP, _VP, _VP]),
+    "vp_adjoint_begin": (C.c_int, [_VP, C.POINTER(vp_params), C.POINTER(vp_ray_source), C.c_int64, _VP, _VP,
+                                   C.POINTER(vp_hit_record), _VP, _VP, _VP, _VP]),
+    "vp_adjoint_finish": (C.c_int, [_VP, C.POINTER(vp_params), C.POINTER(vp_ray_source), C.c_int64,
+                                    C.POINTER(vp_hit_record), C.c_int64, C.c_int64, _VP, _VP, _VP, _VP]),
+    "vp_film_splat": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP]),
+    "vp_film_develop": (C.c_int, [C.c_int32, C.c_int32, _VP, _VP, C.c_int64, _VP]),
+    "vp_film_adjoint": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, C.c_int64, _VP, _VP]),
+    "vp_set_option": (C.c_int, [_VP, C.c_char_p, C.c_int64]),
     "vp_get_stats": (C.c_int, [_VP, C.POINTER(vp_stats), _VP]),
     "vp_bounded_adam_step": (C.c_int, [C.c_int64, _VP, _VP, _VP, _VP, C.c_double, C.c_double, C.c_double, C.c_double,
                                        C.c_int, C.c_float, C.c_int, C.c_float, _VP]),

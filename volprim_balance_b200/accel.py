@@ -13,7 +13,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _cabi
-from ._cabi import VolprimCudaError, vp_camera, vp_params, vp_stats
+from ._cabi import VolprimCudaError, vp_camera, vp_hit_record, vp_params, vp_ray_source, vp_stats
 
 
 def _ptr(t):
@@ -27,11 +27,86 @@ def _f32(t: torch.Tensor, device) -> torch.Tensor:
 
 
 @dataclass
+class RaySource:
+    """Rays of a render call: explicit (o, d, maxt) tensors, or a perspective sensor evaluated inside the trace
+    kernels (`camera` = vp_camera, pixel-major then sample; `rows` = (first row, row count) of a band)."""
+    o: torch.Tensor | None = None
+    d: torch.Tensor | None = None
+    maxt: torch.Tensor | None = None
+    camera: vp_camera | None = None
+    spp: int = 1
+    jitter: torch.Tensor | None = None
+    rows: tuple | None = None
+
+    @property
+    def n_rays(self) -> int:
+        if self.camera is not None:
+            rows = self.rows[1] if self.rows else self.camera.height
+            return self.camera.width * rows * self.spp
+        return self.o.shape[0]
+
+    def to_c(self) -> vp_ray_source:
+        rs = vp_ray_source()
+        if self.camera is not None:
+            rs.camera = C.pointer(self.camera)
+            rs.spp = int(self.spp)
+            rs.jitter = self.jitter.data_ptr() if self.jitter is not None else None
+            if self.rows:
+                rs.row_begin, rs.row_count = int(self.rows[0]), int(self.rows[1])
+        else:
+            rs.ray_o, rs.ray_d = self.o.data_ptr(), self.d.data_ptr()
+            rs.ray_maxt = self.maxt.data_ptr() if self.maxt is not None else None
+            rs.spp = 1
+        return rs
+
+
+class HitRecord:
+    """Ordered hit lists of a primal pass in compressed-row form (vp_hit_record): 4 bytes per recorded hit,
+    8 per ray, 4 per primitive.  `usable()` reads two device counters (synchronises the stream once)."""
+
+    def __init__(self, n_rays: int, n_prims: int, capacity: int, id_cap: int, device):
+        self.n_rays, self.n_prims = n_rays, n_prims
+        self.capacity, self.id_cap = int(max(capacity, 1)), int(id_cap)
+        self.ray_offsets = torch.empty(n_rays + 1, dtype=torch.int64, device=device)
+        self.ids = torch.empty(self.capacity, dtype=torch.int32, device=device)
+        self.prim_offsets = torch.empty(n_prims + 1, dtype=torch.int32, device=device)   # bit pattern of uint32
+        self.total = torch.zeros(2, dtype=torch.int64, device=device)
+        self._usable = None
+
+    def to_c(self) -> vp_hit_record:
+        r = vp_hit_record()
+        r.ray_offsets, r.ids = self.ray_offsets.data_ptr(), self.ids.data_ptr()
+        r.prim_offsets, r.total = self.prim_offsets.data_ptr(), self.total.data_ptr()
+        r.capacity, r.id_cap = self.capacity, self.id_cap
+        return r
+
+    def totals(self):
+        t = self.total.tolist()
+        return int(t[0]), int(t[1])
+
+    def usable(self) -> bool:
+        if self._usable is None:
+            entries, cut = self.totals()
+            self._usable = entries <= self.capacity and cut == 0
+        return self._usable
+
+    def nbytes(self) -> int:
+        return self.ids.numel() * 4 + self.ray_offsets.numel() * 8 + self.prim_offsets.numel() * 4
+
+    def lists(self):
+        """Python view for tests: list of per-ray id arrays (host)."""
+        off = self.ray_offsets.cpu().numpy()
+        ids = self.ids.cpu().numpy()
+        return [ids[off[r]:off[r + 1]] for r in range(self.n_rays)]
+
+
+@dataclass
 class TraceResult:
     rgb: torch.Tensor        # [R, 3]
     beta: torch.Tensor       # [R] final throughput
     nhits: torch.Tensor      # [R] int32 (bit pattern of uint32)
     hit_ids: torch.Tensor | None = None  # [cap, R] int32, -1 padded (hit-major: coalesced per hit index)
+    record: HitRecord | None = None      # compressed-row lists (render_forward(record=True))
 
 
 class EllipsoidAccel:
@@ -48,6 +123,7 @@ class EllipsoidAccel:
         self.n = 0
         self.sh_floats = 0
         self.built = False
+        self.hits_per_ray_estimate = 48.0   # sizes the next hit record; follows the records actually produced
 
     def close(self):
         if getattr(self, "_h", None):
@@ -108,7 +184,8 @@ class EllipsoidAccel:
         rgb = torch.empty((R, 3), dtype=torch.float32, device=self.device)
         beta = torch.empty((R,), dtype=torch.float32, device=self.device)
         nhits = torch.empty((R,), dtype=torch.int32, device=self.device)
-        ids = torch.empty((record_cap, R), dtype=torch.int32, device=self.device) if record_cap > 0 else None
+        # the kernel writes only the entries a ray has; the dense debug / parity view is pre-filled with -1
+        ids = torch.full((record_cap, R), -1, dtype=torch.int32, device=self.device) if record_cap > 0 else None
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.vp_trace_forward(self._h, C.byref(params), R, _ptr(o), _ptr(d), _ptr(maxt_t),
                                                    _ptr(rgb), _ptr(beta), _ptr(nhits), _ptr(ids), record_cap, 1, R,
@@ -142,6 +219,111 @@ class EllipsoidAccel:
                                                    _ptr(dL), _ptr(st), _ptr(hit_ids), _ptr(hit_counts), cap, 1, R,
                                                    _ptr(g_data), _ptr(g_attr), _ptr(g_sh), self._stream()), self._h)
         return g_data, g_attr, g_sh
+
+    # -- sensor-fused / record-replay path (what render() uses) ------------------------------------------
+    def set_option(self, name: str, value: int):
+        _cabi.check(self._lib.vp_set_option(self._h, name.encode(), int(value)), self._h)
+
+    def new_record(self, n_rays: int, id_cap: int, capacity: int | None = None) -> HitRecord:
+        if capacity is None:
+            capacity = int(n_rays * min(float(id_cap), self.hits_per_ray_estimate * 1.3 + 4.0)) + 4096
+        capacity = min(capacity, (1 << 32) - 1)
+        return HitRecord(n_rays, self.n, capacity, id_cap, self.device)
+
+    def render_forward(self, params: vp_params, rays: RaySource, record=None, id_cap: int = 0,
+                       want_beta: bool = True, want_nhits: bool = True) -> TraceResult:
+        """vp_render_forward.  `record`: None / False, True (a HitRecord sized from the running estimate is
+        allocated) or a HitRecord to fill."""
+        R = rays.n_rays
+        rgb = torch.empty((R, 3), dtype=torch.float32, device=self.device)
+        beta = torch.empty((R,), dtype=torch.float32, device=self.device) if want_beta else None
+        nhits = torch.empty((R,), dtype=torch.int32, device=self.device) if want_nhits else None
+        rec = None
+        if record is True:
+            rec = self.new_record(R, id_cap)
+        elif isinstance(record, HitRecord):
+            rec = record
+            rec._usable = None
+        crec = rec.to_c() if rec is not None else None
+        crays = rays.to_c()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.vp_render_forward(self._h, C.byref(params), C.byref(crays), R, _ptr(rgb), _ptr(beta),
+                                                    _ptr(nhits), C.byref(crec) if crec is not None else None,
+                                                    self._stream()), self._h)
+        return TraceResult(rgb, beta, nhits, None, rec)
+
+    def _grad_out(self, out):
+        if out is not None:
+            return out
+        g_data = torch.zeros(self.n * 10, dtype=torch.float32, device=self.device)
+        g_attr = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        g_sh = torch.zeros(self.n * self.sh_floats, dtype=torch.float32, device=self.device) if self.sh_floats else None
+        return g_data, g_attr, g_sh
+
+    def render_adjoint(self, params: vp_params, rays: RaySource, dL, state_in, record: HitRecord, out=None):
+        """vp_render_adjoint: replay `record`; volprim_rf gathers per primitive (no global reductions).  The caller
+        checks record.usable() first (an unusable record makes the kernels return without touching the gradients)."""
+        g_data, g_attr, g_sh = self._grad_out(out)
+        R = rays.n_rays
+        dL, st = _f32(dL, self.device).reshape(-1, 3), _f32(state_in, self.device).reshape(-1, 3)
+        if dL.shape[0] != R or st.shape[0] != R:
+            raise ValueError("d_L / state_in must have one RGB triple per ray")
+        crec, crays = record.to_c(), rays.to_c()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.vp_render_adjoint(self._h, C.byref(params), C.byref(crays), R, _ptr(dL), _ptr(st),
+                                                    C.byref(crec), _ptr(g_data), _ptr(g_attr), _ptr(g_sh),
+                                                    self._stream()), self._h)
+        return g_data, g_attr, g_sh
+
+    def adjoint_begin(self, params: vp_params, rays: RaySource, dL, state_in, record: HitRecord, out):
+        g_data, g_attr, g_sh = out
+        R = rays.n_rays
+        dL, st = _f32(dL, self.device).reshape(-1, 3), _f32(state_in, self.device).reshape(-1, 3)
+        crec, crays = record.to_c(), rays.to_c()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.vp_adjoint_begin(self._h, C.byref(params), C.byref(crays), R, _ptr(dL), _ptr(st),
+                                                   C.byref(crec), _ptr(g_data), _ptr(g_attr), _ptr(g_sh),
+                                                   self._stream()), self._h)
+
+    def adjoint_finish(self, params: vp_params, rays: RaySource, record: HitRecord, prim_begin: int, prim_end: int, out):
+        g_data, g_attr, g_sh = out
+        crec, crays = record.to_c(), rays.to_c()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.vp_adjoint_finish(self._h, C.byref(params), C.byref(crays), rays.n_rays, C.byref(crec),
+                                                    int(prim_begin), int(prim_end), _ptr(g_data), _ptr(g_attr),
+                                                    _ptr(g_sh), self._stream()), self._h)
+
+    def note_record(self, record: HitRecord):
+        """Feed the size of a finished record back into the estimate that sizes the next one."""
+        entries, _ = record.totals()
+        if record.n_rays:
+            self.hits_per_ray_estimate = max(4.0, entries / record.n_rays)
+
+    # -- film ------------------------------------------------------------------------------------
+    def film_splat(self, width, height, spp, rfilter: int, jitter, radiance, accum):
+        with torch.cuda.device(self.device):
+            rc = self._lib.vp_film_splat(width, height, spp, rfilter, _ptr(jitter), _ptr(radiance), _ptr(accum), self._stream())
+        if rc:
+            raise VolprimCudaError(f"vp_film_splat failed ({rc})")
+
+    def film_develop(self, width, height, accum, image_view):
+        """image_view: [H, W, 3] float32 view with unit element stride in the last two dims (a column block of a
+        batch film is fine: the row stride is passed on)."""
+        assert image_view.stride(2) == 1 and image_view.stride(1) == 3
+        with torch.cuda.device(self.device):
+            rc = self._lib.vp_film_develop(width, height, _ptr(accum), _ptr(image_view), image_view.stride(0), self._stream())
+        if rc:
+            raise VolprimCudaError(f"vp_film_develop failed ({rc})")
+
+    def film_adjoint(self, width, height, spp, rfilter: int, jitter, accum, d_image_view):
+        assert d_image_view.stride(2) == 1 and d_image_view.stride(1) == 3
+        dL = torch.empty((width * height * spp, 3), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.vp_film_adjoint(width, height, spp, rfilter, _ptr(jitter), _ptr(accum), _ptr(d_image_view),
+                                           d_image_view.stride(0), _ptr(dL), self._stream())
+        if rc:
+            raise VolprimCudaError(f"vp_film_adjoint failed ({rc})")
+        return dL
 
     def raygen_perspective(self, cam: vp_camera, spp: int = 1, jitter=None):
         total = cam.width * cam.height * spp

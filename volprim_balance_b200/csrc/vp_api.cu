@@ -115,7 +115,8 @@ int vp_destroy(vp_ctx *ctx)
     DevBuffer *all[] = { &ctx->raw_data, &ctx->raw_attr, &ctx->raw_sh, &ctx->geo0, &ctx->geo1, &ctx->geo2, &ctx->sh4, &ctx->xf, &ctx->info,
                          &ctx->nodes, &ctx->perm, &ctx->inv_perm, &ctx->leaf_lo, &ctx->leaf_hi, &ctx->keys[0],
                          &ctx->keys[1], &ctx->vals[0], &ctx->vals[1], &ctx->hist, &ctx->parent, &ctx->counters,
-                         &ctx->bounds, &ctx->stats };
+                         &ctx->bounds, &ctx->stats, &ctx->scan_tmp, &ctx->rec_dense, &ctx->rec_counts, &ctx->rec_nhits,
+                         &ctx->adj_cursor, &ctx->adj_state, &ctx->adj_ray };
     for (DevBuffer *b : all) free_buf(*b);
     delete ctx;
     return VP_OK;
@@ -194,6 +195,72 @@ int vp_raygen_perspective(vp_ctx *ctx, const vp_camera *cam, int32_t spp, const 
     if (!ctx) return VP_E_INVALID;
     DeviceGuard g(ctx->device);
     return vp_raygen_impl(ctx, cam, spp, jitter, ray_o, ray_d, ray_maxt, (cudaStream_t)stream);
+}
+
+int vp_render_forward(vp_ctx *ctx, const vp_params *params, const vp_ray_source *rays, int64_t n_rays, float *out_rgb,
+                      float *out_T, uint32_t *out_nhits, const vp_hit_record *record, void *stream)
+{
+    if (!ctx) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    return vp_render_forward_impl(ctx, params, rays, n_rays, out_rgb, out_T, out_nhits, record, (cudaStream_t)stream);
+}
+
+int vp_adjoint_begin(vp_ctx *ctx, const vp_params *params, const vp_ray_source *rays, int64_t n_rays, const float *d_L,
+                     const float *state_in, const vp_hit_record *record, float *g_data10, float *g_attr, float *g_sh,
+                     void *stream)
+{
+    if (!ctx) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    return vp_adjoint_begin_impl(ctx, params, rays, n_rays, d_L, state_in, record, g_data10, g_attr, g_sh, (cudaStream_t)stream);
+}
+
+int vp_adjoint_finish(vp_ctx *ctx, const vp_params *params, const vp_ray_source *rays, int64_t n_rays,
+                      const vp_hit_record *record, int64_t prim_begin, int64_t prim_end, float *g_data10, float *g_attr,
+                      float *g_sh, void *stream)
+{
+    if (!ctx) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    return vp_adjoint_finish_impl(ctx, params, rays, n_rays, record, prim_begin, prim_end, g_data10, g_attr, g_sh,
+                                  (cudaStream_t)stream);
+}
+
+int vp_render_adjoint(vp_ctx *ctx, const vp_params *params, const vp_ray_source *rays, int64_t n_rays, const float *d_L,
+                      const float *state_in, const vp_hit_record *record, float *g_data10, float *g_attr, float *g_sh,
+                      void *stream)
+{
+    if (!ctx) return VP_E_INVALID;
+    DeviceGuard g(ctx->device);
+    int rc = vp_adjoint_begin_impl(ctx, params, rays, n_rays, d_L, state_in, record, g_data10, g_attr, g_sh, (cudaStream_t)stream);
+    if (rc) return rc;
+    return vp_adjoint_finish_impl(ctx, params, rays, n_rays, record, 0, ctx->n, g_data10, g_attr, g_sh, (cudaStream_t)stream);
+}
+
+int vp_film_splat(int32_t width, int32_t height, int32_t spp, int32_t rfilter, const float *jitter, const float *radiance,
+                  float *accum, void *stream)
+{
+    return vp_film_splat_impl(width, height, spp, rfilter, jitter, radiance, accum, (cudaStream_t)stream);
+}
+
+int vp_film_develop(int32_t width, int32_t height, const float *accum, float *image, int64_t image_row_stride, void *stream)
+{
+    return vp_film_develop_impl(width, height, accum, image, image_row_stride, (cudaStream_t)stream);
+}
+
+int vp_film_adjoint(int32_t width, int32_t height, int32_t spp, int32_t rfilter, const float *jitter, const float *accum,
+                    const float *d_image, int64_t d_image_row_stride, float *d_L, void *stream)
+{
+    return vp_film_adjoint_impl(width, height, spp, rfilter, jitter, accum, d_image, d_image_row_stride, d_L, (cudaStream_t)stream);
+}
+
+int vp_set_option(vp_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name) return VP_E_INVALID;
+    if (!std::strcmp(name, "record_scratch_bytes")) {
+        if (value < (1 << 20)) return vp_fail(ctx, VP_E_INVALID, "vp_set_option: record_scratch_bytes must be at least 1 MiB");
+        ctx->record_scratch_bytes = value;
+        return VP_OK;
+    }
+    return vp_fail(ctx, VP_E_INVALID, std::string("vp_set_option: unknown option '") + name + "'");
 }
 
 int vp_get_stats(vp_ctx *ctx, vp_stats *host_out, void *stream)

@@ -7,7 +7,7 @@
 //
 //   1. scene bounds of the centres            (block reduce + ordered-uint atomics)
 //   2. 63-bit Morton code per primitive
-//   3. LSD radix sort of (code, index), 8 bits per pass, hand-written (histogram / scan / ranked scatter)
+//   3. LSD radix sort of (code, index), 8 bits per pass, hand-written (tile histogram / multi-block scan / ranked scatter)
 //   4. gather the reference AoS records into the Morton-ordered 128-bit SoA + leaf boxes
 //   5. Karras hierarchy over the sorted codes
 //   6. bottom-up box fit with per-node arrival counters
@@ -19,6 +19,7 @@
 //   [12] left link    [13] right link   [14] parent        [15] unused
 // A link >= 0 is an internal node, a link < 0 is the leaf ~link (= sorted primitive position).
 #include "vp_internal.cuh"
+#include "vp_scan.cuh"
 
 #include <cfloat>
 
@@ -122,51 +123,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint64_t *__r
     for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) hist[(size_t)i * n_tiles + blockIdx.x] = sh[i];
 }
 
-// 3b. exclusive scan of the digit-major histogram (single block; the array has 256 * n_tiles entries)
-__global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ hist, int total)
-{
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < total; base += 1024 * 4) {
-        int i0 = base + threadIdx.x * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < total) ? hist[i0 + k] : 0u;
-        uint32_t s = v[0] + v[1] + v[2] + v[3];
-        uint32_t incl = s;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += t;
-        }
-        if (lane == 31) warp_sums[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t w = warp_sums[lane];
-            uint32_t wi = w;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, wi, off);
-                if (lane >= off) wi += t;
-            }
-            warp_sums[lane] = wi - w;  // exclusive
-        }
-        __syncthreads();
-        uint32_t carry = carry_s;
-        uint32_t excl = carry + warp_sums[wid] + (incl - s);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k < total) hist[i0 + k] = excl;
-            excl += v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + warp_sums[31] + incl;
-        __syncthreads();
-    }
-}
+// 3b. exclusive scan of the digit-major histogram [256 * n_tiles]: vpscan::exclusive_scan (multi-block, vp_scan.cuh)
 
 // 3c. stable ranked scatter.  Each warp owns a contiguous 512-key slice of the tile and walks it in
 // 32-key rounds; __match_any_sync groups equal digits, the group's lowest lane owns the counter.
@@ -299,9 +256,10 @@ __global__ void k_gather_soa(const float *__restrict__ data10, const float *__re
     }
     // mean projected area of the leaf box = surface area / 4 (feeds the initial interval width)
     float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
-    if (isfinite(ex) && isfinite(ey) && isfinite(ez) && ex > 0.f && ey > 0.f && ez > 0.f)
+    if (isfinite(ex) && isfinite(ey) && isfinite(ez) && ex > 0.f && ey > 0.f && ez > 0.f) {
         area = 0.5f * (ex * ey + ey * ez + ez * ex);
         half = (ex + ey + ez) * (1.f / 6.f);
+    }
     }
     for (int off = 16; off; off >>= 1) area += __shfl_xor_sync(0xffffffffu, area, off);
     if ((threadIdx.x & 31) == 0 && area > 0.f) atomicAdd(info + 7, area);
@@ -464,6 +422,7 @@ int vp_build_impl(vp_ctx *ctx, bool refit_only, cudaStream_t st)
     const int n_tiles = cdiv(n, SORT_TILE);
     if ((rc = vp_ensure(ctx, ctx->hist, sizeof(uint32_t) * (size_t)RADIX * n_tiles))) return rc;
     if ((rc = vp_ensure(ctx, ctx->bounds, sizeof(uint32_t) * 8))) return rc;
+    if ((rc = vp_ensure(ctx, ctx->scan_tmp, sizeof(uint64_t) * (size_t)(vpscan::n_tiles((int64_t)RADIX * n_tiles) + 1)))) return rc;
 
     const float *data10 = (const float *)ctx->raw_data.ptr;
     const float *attr = ctx->have_attr ? (const float *)ctx->raw_attr.ptr : nullptr;
@@ -483,7 +442,7 @@ int vp_build_impl(vp_ctx *ctx, bool refit_only, cudaStream_t st)
             uint32_t *vin = (uint32_t *)ctx->vals[cur].ptr, *vout = (uint32_t *)ctx->vals[cur ^ 1].ptr;
             uint32_t *hist = (uint32_t *)ctx->hist.ptr;
             k_radix_hist<<<n_tiles, SORT_THREADS, 0, st>>>(kin, n, shift, n_tiles, hist);
-            k_radix_scan<<<1, 1024, 0, st>>>(hist, RADIX * n_tiles);
+            vpscan::exclusive_scan<uint32_t>(hist, (int64_t)RADIX * n_tiles, hist, (uint32_t *)ctx->scan_tmp.ptr, nullptr, nullptr, st);
             k_radix_scatter<<<n_tiles, SORT_THREADS, 0, st>>>(kin, vin, n, shift, n_tiles, hist, kout, vout);
             cur ^= 1;
         }

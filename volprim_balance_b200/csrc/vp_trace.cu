@@ -26,6 +26,7 @@
 //   retry with a shorter interval; below a minimum width the per-ray walker runs a plain closest-hit search per step.
 // The adjoint either replays recorded hit lists (no BVH access) or re-traces like the primal.
 #include "vp_internal.cuh"
+#include "vp_scan.cuh"
 
 #include <cfloat>
 #include <cmath>
@@ -875,6 +876,14 @@ __device__ __forceinline__ void sh_basis(float3 d, float (&Y)[(D + 1) * (D + 1)]
     }
 }
 
+// 256-bit read-only global load (LDG.E.256 on sm_100a); p must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b)
+{
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+
 // eval_sh_emission (rf:82-100): raw = sum_i Y_i f_i + 0.5 ; col = max(raw, 0).  128-bit loads of the
 // primitive's contiguous coefficient block.
 template <int D>
@@ -886,8 +895,18 @@ __device__ __forceinline__ void sh_color(const DevScene &S, int pos, const float
     const float4 *f = S.sh4 + (size_t)pos * N4;
     float acc[3] = { 0.f, 0.f, 0.f };
     float4 v[N4];
+#ifdef VP_SH_LDG256
+    // sm_100 has 256-bit global loads: the coefficient block of a primitive (192 B at degree 3, 32-byte aligned when
+    // N4 is even) takes half as many load instructions -- and half as many L1 wavefronts, the co-limiter of the drain
+    if constexpr (N4 % 2 == 0) {
 #pragma unroll
-    for (int k = 0; k < N4; ++k) v[k] = __ldg(f + k);
+        for (int k = 0; k < N4; k += 2) ldg256(f + k, v[k], v[k + 1]);
+    } else
+#endif
+    {
+#pragma unroll
+        for (int k = 0; k < N4; ++k) v[k] = __ldg(f + k);
+    }
 #pragma unroll
     for (int k = 0; k < N4; ++k) {
         const float e[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
@@ -990,6 +1009,31 @@ __device__ __forceinline__ float srgb_to_linear(float x)
     return x <= 0.04045f ? x / 12.92f : powf((x + 0.055f) / 1.055f, 2.4f);
 }
 
+// sampler.next_1d() of Mitsuba's `independent` sampler, random access (third-party, restated from the published
+// algorithms; identical to oracle/volprim_oracle.c pcg32_float_at): PCG32 stream per ray, seeded with
+// sample_tea_32(seed, ray index).  No per-ray generator state is carried through the walk: Russian roulette draws
+// a handful of samples per ray, each recomputed from the seed (one 64-bit multiply-add per skipped sample).
+__device__ __forceinline__ float pcg32_float_at(uint32_t seed, uint32_t idx, uint32_t n)
+{
+    uint32_t v0 = seed, v1 = idx, sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    const unsigned long long mult = 0x5851f42d4c957f2dull;
+    const unsigned long long inc = ((unsigned long long)v1 << 1) | 1ull;
+    unsigned long long state = inc;          // state = 0 * mult + inc
+    state += (unsigned long long)v0;
+    state = state * mult + inc;
+    for (uint32_t i = 0; i < n; ++i) state = state * mult + inc;
+    const uint32_t xorshifted = (uint32_t)(((state >> 18) ^ state) >> 27);
+    const uint32_t rot = (uint32_t)(state >> 59);
+    const uint32_t out = (xorshifted >> rot) | (xorshifted << ((0u - rot) & 31u));
+    return __uint_as_float((out >> 9) | 0x3f800000u) - 1.f;
+}
+
 // thread -> ray index; with an image hint the 32 lanes of a warp cover an 8x4 pixel tile
 __device__ __forceinline__ int64_t ray_index(int64_t t, int W, int H)
 {
@@ -1021,19 +1065,78 @@ __device__ __forceinline__ void flush_counters(const Counters &cn, vp_stats *st)
     }
 }
 
+// Where a kernel takes its rays from: explicit arrays, or a perspective sensor evaluated in the kernel (fused
+// Sensor.sample_ray; volprim/cameras.py:114-137 configures the Mitsuba `perspective` plugin this restates).
+struct RaySrc {
+    const float *o, *d, *maxt, *jitter;
+    vp_camera cam;
+    float tan_half;        // tan(fov_x / 2), computed once on the host in double
+    int32_t has_cam, spp;
+    int64_t index_base;    // ray i of the call is sample (index_base + i) of the sensor (row bands, record bands)
+};
+
+// One ray of a perspective sensor: sample index gi = pixel * spp + sample, pixel row-major.  Every operation is
+// individually rounded so that the stand-alone ray generation kernel and the fused paths produce identical rays.
+__device__ __forceinline__ void camera_ray(const RaySrc &S, int64_t i, float3 &o, float3 &d, float &maxt)
+{
+    const vp_camera &cam = S.cam;
+    const int64_t gi = S.index_base + i;
+    const int64_t pix = gi / S.spp;
+    const int x = (int)(pix % cam.width), y = (int)(pix / cam.width);
+    float jx = 0.5f, jy = 0.5f;
+    if (S.jitter) { jx = S.jitter[2 * i]; jy = S.jitter[2 * i + 1]; }
+    const float u = __fdiv_rn(__fadd_rn((float)x, jx), (float)cam.width);
+    const float v = __fdiv_rn(__fadd_rn((float)y, jy), (float)cam.height);
+    const float aspect = __fdiv_rn((float)cam.width, (float)cam.height);
+    // Mitsuba perspective sensor: +z forward, +x to the LEFT of the image, +y up
+    const float lx = __fmul_rn(__fadd_rn(__fsub_rn(1.f, __fmul_rn(2.f, u)), __fmul_rn(2.f, cam.cx)), S.tan_half);
+    const float ly = __fdiv_rn(__fmul_rn(__fadd_rn(__fsub_rn(1.f, __fmul_rn(2.f, v)), __fmul_rn(2.f, cam.cy)), S.tan_half), aspect);
+    const float inv_n = __frcp_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(lx, lx), __fmul_rn(ly, ly)), 1.f)));
+    const float3 dl = make_float3(__fmul_rn(lx, inv_n), __fmul_rn(ly, inv_n), inv_n);
+    const float *m = cam.to_world;
+    d = make_float3(__fadd_rn(__fadd_rn(__fmul_rn(m[0], dl.x), __fmul_rn(m[1], dl.y)), __fmul_rn(m[2], dl.z)),
+                    __fadd_rn(__fadd_rn(__fmul_rn(m[4], dl.x), __fmul_rn(m[5], dl.y)), __fmul_rn(m[6], dl.z)),
+                    __fadd_rn(__fadd_rn(__fmul_rn(m[8], dl.x), __fmul_rn(m[9], dl.y)), __fmul_rn(m[10], dl.z)));
+    const float inv_z = __frcp_rn(dl.z);
+    const float near_t = __fmul_rn(cam.near_clip, inv_z), far_t = __fmul_rn(cam.far_clip, inv_z);
+    o = make_float3(__fmaf_rn(d.x, near_t, m[3]), __fmaf_rn(d.y, near_t, m[7]), __fmaf_rn(d.z, near_t, m[11]));
+    maxt = __fsub_rn(far_t, near_t);
+}
+
+__device__ __forceinline__ void load_ray(const RaySrc &S, int64_t r, float3 &o, float3 &d, float &maxt)
+{
+    if (S.has_cam) { camera_ray(S, r, o, d, maxt); return; }
+    o = make_float3(S.o[3 * r], S.o[3 * r + 1], S.o[3 * r + 2]);
+    d = make_float3(S.d[3 * r], S.d[3 * r + 1], S.d[3 * r + 2]);
+    maxt = S.maxt ? S.maxt[r] : FLT_MAX;
+}
+
+// per-hit state the ray-major pass of the gather adjoint leaves in the bucket of the hit primitive
+struct GatherBuf {
+    const uint32_t *prim_offsets;   // [N + 1] bucket starts (exclusive prefix of the recorded hit counts)
+    uint32_t *cursor;               // [N] entries written so far
+    float4 *state;                  // (dcol.rgb, dalpha)
+    uint32_t *ray;                  // ray index of the entry
+    const int64_t *total;           // record validity: total[0] <= capacity && total[1] == 0
+    int64_t capacity;
+};
+
 struct TraceArgs {
     int64_t R;
-    const float *o, *d, *maxt;
+    RaySrc src;
     float *rgb, *T;
     uint32_t *nhits;
-    int32_t *ids;
+    int32_t *ids;            // forward: hit-id output (dense, strides rs / hs)
     int32_t cap;
     int64_t rs, hs;
+    uint32_t *prim_counts;   // forward, optional: recorded hits per primitive (original numbering)
     // adjoint
     const float *dL, *state_in;
-    const int32_t *rec_ids;
+    const int32_t *rec_ids;       // replay: dense (rs, hs, rec_counts, cap) or compressed rows (rec_offsets, stride 1)
     const uint32_t *rec_counts;
+    const int64_t *rec_offsets;
     float *g_data, *g_attr, *g_sh;
+    GatherBuf gb;
     vp_stats *stats;
 };
 
@@ -1050,11 +1153,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
     const int64_t r = in_range ? ray_index(t, P.image_width, P.image_height) : 0;
     float3 o = make_float3(0.f, 0.f, 0.f), d = make_float3(0.f, 0.f, 1.f);
     float maxt = FLT_MAX;
-    if (in_range) {
-        o = make_float3(A.o[3 * r], A.o[3 * r + 1], A.o[3 * r + 2]);
-        d = make_float3(A.d[3 * r], A.d[3 * r + 1], A.d[3 * r + 2]);
-        if (A.maxt) maxt = A.maxt[r];
-    }
+    if (in_range) load_ray(A.src, r, o, d, maxt);
     const float3 o0 = walker_origin<TILE>(S, o, d, in_range);
     float beta = 1.f, L[3] = { 0.f, 0.f, 0.f };
     uint32_t depth = 0;
@@ -1087,7 +1186,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
             T = expf(-rho * g0.w);                      // tomo:44
         }
         beta *= T;                                      // rf:146 / tomo:85
-        if (A.ids && depth < (uint32_t)A.cap) A.ids[r * A.rs + depth * A.hs] = __float_as_int(g1.w);
+        if (A.ids && depth < (uint32_t)A.cap) {
+            A.ids[r * A.rs + depth * A.hs] = __float_as_int(g1.w);
+            if (A.prim_counts) atomicAdd(A.prim_counts + __float_as_int(g1.w), 1u);   // bucket sizes of the gather adjoint
+        }
         // ray.o = si.p + ray.d * 1e-4                     rf:149 / tomo:114
         o.x = fmaf(d.x, P.eps_advance, fmaf(d.x, is.tn, o.x));
         o.y = fmaf(d.y, P.eps_advance, fmaf(d.y, is.tn, o.y));
@@ -1095,6 +1197,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
         depth += 1;
         cn.hits++;
         if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) return false;  // rf:173-174
+        if (INTEG == VP_INTEGRATOR_RF && P.use_rr) {                          // rf:177-183 (primal pass only)
+            const float rr_prob = fmaxf(beta, 0.1f);
+            if (depth >= P.rr_depth && beta < 0.1f) {
+                beta *= __fdiv_rn(1.f, rr_prob);
+                // the sampler advances once per loop iteration: this one drew sample rr_skip + depth - 1 of the ray's stream
+                const float u = pcg32_float_at(P.rr_seed, (uint32_t)(A.src.index_base + r), P.rr_skip + depth - 1u);
+                if (!(u < rr_prob)) return false;
+            }
+        }
         if (!(depth < P.max_depth)) return false;                             // rf:186
         return true;
     };
@@ -1115,8 +1226,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
         A.rgb[3 * r + 2] = L[2];
         if (A.T) A.T[r] = beta;
         if (A.nhits) A.nhits[r] = depth;
-        if (A.ids)
-            for (uint32_t k = depth; k < (uint32_t)A.cap; ++k) A.ids[r * A.rs + k * A.hs] = -1;
+        // (hit lists are not padded: a ray's entries beyond its count are never read -- 75 % of the dense block on
+        // the headline configuration used to be -1 fill)
     }
     flush_counters(cn, A.stats);
 }
@@ -1144,20 +1255,26 @@ __device__ __forceinline__ void scatter_geo(float *g_data, int orig, const float
     for (int k = 0; k < 5; ++k) atomicAdd(dst + k, make_float2(g10[2 * k], g10[2 * k + 1]));
 }
 
-// one rf interaction of the adjoint; returns T
+// Per-hit coefficients of the rf adjoint: everything that depends on the ray's running state
+// (beta, remaining radiance).  Given these, the gradient of the hit is a function of (ray, primitive) alone.
+struct RfCoeffs {
+    float T, G, op;
+    float3 pp;        // p_peak
+    float dalpha;     // d loss / d alpha  (before the 0.9999 clamp of alpha)
+    float dcol[3];    // d loss / d colour, zero where the colour is clamped at 0
+};
+
 template <int KERNEL, int D>
-__device__ __forceinline__ float rf_adjoint_hit(const DevScene &S, const TraceArgs &A, int pos, float3 o, float3 d,
-                                                float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is,
-                                                float beta, const float (&g)[3], float (&L)[3],
-                                                const float (&Y)[(D >= 0) ? (D + 1) * (D + 1) : 1])
+__device__ __forceinline__ RfCoeffs rf_adjoint_coeffs(const DevScene &S, int pos, float3 o, float3 d, float4 g0, float4 g1,
+                                                      const Mat3 &Rm, const Isect &is, float beta, const float (&g)[3],
+                                                      float (&L)[3], const float (&Y)[(D >= 0) ? (D + 1) * (D + 1) : 1])
 {
-    constexpr int NB = (D >= 0) ? (D + 1) * (D + 1) : 0;
-    const int orig = __float_as_int(g1.w);
+    RfCoeffs c;
     RfEval e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
     float raw[3] = { 0.f, 0.f, 0.f };
     if constexpr (D >= 0) sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw);
     const float omt = 1.f - e.T;
-    float dalpha = 0.f, dcol[3];
+    float dalpha = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         float col = (D >= 0) ? fmaxf(raw[ch], 0.f) : 0.f;
@@ -1166,48 +1283,69 @@ __device__ __forceinline__ float rf_adjoint_hit(const DevScene &S, const TraceAr
         if (!lef) le = 0.f;
         L[ch] -= le;                                  // rf:145 (adjoint branch)
         float lo = le + L[ch] * e.T / e.T;            // rf:156-159
-        dcol[ch] = 0.f;
+        c.dcol[ch] = 0.f;
         if (isfinite(lo)) {                           // rf:160
             if (lef) {
                 dalpha += g[ch] * beta * col;
-                if (raw[ch] > 0.f) dcol[ch] = g[ch] * beta * omt;
+                if (raw[ch] > 0.f) c.dcol[ch] = g[ch] * beta * omt;
             }
             dalpha -= g[ch] * L[ch] / e.T;
         }
     }
+    c.T = e.T; c.G = e.G; c.op = e.op; c.pp = e.pp; c.dalpha = dalpha;
+    return c;
+}
+
+// geometry terms of one hit: with dq = d loss / d q (q = |diag(1/(k s)) R^T (p_peak - c)|^2; d q / d t_peak = 0 at the
+// peak), dw_i = 2 w_i / (k s_i)^2 dq.  d center = -R dw, d scale_i = -w_i dw_i / s_i, d R_ab = v_a dw_b.
+template <int KERNEL>
+__device__ __forceinline__ bool rf_geo_terms(float4 g0, float4 g1, const Mat3 &Rm, float3 pp, float G, float op, float dalpha,
+                                             float3 &v, float3 &w, float (&dw)[3])
+{
+    const float dG = dalpha * op;
+    float dq, k2 = 1.f;
+    if (KERNEL == VP_KERNEL_GAUSSIAN) dq = -0.5f * G * dG;
+    else { dq = (G > 0.f) ? -0.75f * dG : 0.f; k2 = 9.f; }
+    if (dq == 0.f) return false;
+    v = make_float3(pp.x - g0.x, pp.y - g0.y, pp.z - g0.z);
+    w = vp_rot_t_mul_rn(Rm, v);
+    const float sx2 = k2 * g1.x * g1.x, sy2 = k2 * g1.y * g1.y, sz2 = k2 * g1.z * g1.z;
+    dw[0] = 2.f * w.x / sx2 * dq; dw[1] = 2.f * w.y / sy2 * dq; dw[2] = 2.f * w.z / sz2 * dq;
+    return true;
+}
+
+// scatter formulation: the gradient of one hit goes to the reference-layout buffers with vector reductions
+template <int KERNEL, int D>
+__device__ __forceinline__ void rf_scatter_hit(const TraceArgs &A, float4 g0, float4 g1, float4 g2, const Mat3 &Rm,
+                                               const RfCoeffs &c, const float (&Y)[(D >= 0) ? (D + 1) * (D + 1) : 1])
+{
+    constexpr int NB = (D >= 0) ? (D + 1) * (D + 1) : 0;
+    const int orig = __float_as_int(g1.w);
     if constexpr (D >= 0) {
-        if (A.g_sh && (dcol[0] != 0.f || dcol[1] != 0.f || dcol[2] != 0.f)) {
+        if (A.g_sh && (c.dcol[0] != 0.f || c.dcol[1] != 0.f || c.dcol[2] != 0.f)) {
             constexpr int C = 3 * NB;
             float *dst = A.g_sh + (size_t)orig * C;
             if constexpr (C % 4 == 0) {
 #pragma unroll
                 for (int k = 0; k < C / 4; ++k) {
                     float4 v;
-                    v.x = Y[(4 * k + 0) / 3] * dcol[(4 * k + 0) % 3];
-                    v.y = Y[(4 * k + 1) / 3] * dcol[(4 * k + 1) % 3];
-                    v.z = Y[(4 * k + 2) / 3] * dcol[(4 * k + 2) % 3];
-                    v.w = Y[(4 * k + 3) / 3] * dcol[(4 * k + 3) % 3];
+                    v.x = Y[(4 * k + 0) / 3] * c.dcol[(4 * k + 0) % 3];
+                    v.y = Y[(4 * k + 1) / 3] * c.dcol[(4 * k + 1) % 3];
+                    v.z = Y[(4 * k + 2) / 3] * c.dcol[(4 * k + 2) % 3];
+                    v.w = Y[(4 * k + 3) / 3] * c.dcol[(4 * k + 3) % 3];
                     atomicAdd(reinterpret_cast<float4 *>(dst) + k, v);
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < C; ++k) atomicAdd(dst + k, Y[k / 3] * dcol[k % 3]);
+                for (int k = 0; k < C; ++k) atomicAdd(dst + k, Y[k / 3] * c.dcol[k % 3]);
             }
         }
     }
-    if (e.op * e.G < 0.9999f) {                       // dr.minimum passes the gradient to opacity * density
-        atomicAdd(A.g_attr + orig, dalpha * e.G);
-        float dG = dalpha * e.op;
-        float dq = 0.f;
-        float k2 = 1.f;
-        if (KERNEL == VP_KERNEL_GAUSSIAN) dq = -0.5f * e.G * dG;
-        else { dq = (e.G > 0.f) ? -0.75f * dG : 0.f; k2 = 9.f; }
-        if (dq != 0.f) {
-            // q = sum_i w_i^2 / (k s_i)^2, w = R^T v, v = p_peak - c ; dq/dt_peak = 0 at the peak
-            float3 v = make_float3(e.pp.x - g0.x, e.pp.y - g0.y, e.pp.z - g0.z);
-            float3 w = vp_rot_t_mul_rn(Rm, v);
-            float sx2 = k2 * g1.x * g1.x, sy2 = k2 * g1.y * g1.y, sz2 = k2 * g1.z * g1.z;
-            float dw[3] = { 2.f * w.x / sx2 * dq, 2.f * w.y / sy2 * dq, 2.f * w.z / sz2 * dq };
+    if (c.op * c.G < 0.9999f) {                       // dr.minimum passes the gradient to opacity * density
+        atomicAdd(A.g_attr + orig, c.dalpha * c.G);
+        float3 v, w;
+        float dw[3];
+        if (rf_geo_terms<KERNEL>(g0, g1, Rm, c.pp, c.G, c.op, c.dalpha, v, w, dw)) {
             float g10[10];
             g10[3] = -w.x * dw[0] / g1.x;
             g10[4] = -w.y * dw[1] / g1.y;
@@ -1226,7 +1364,16 @@ __device__ __forceinline__ float rf_adjoint_hit(const DevScene &S, const TraceAr
             scatter_geo(A.g_data, orig, g10);
         }
     }
-    return e.T;
+}
+
+// gather formulation, ray-major pass: the per-hit coefficients go to the bucket of the hit primitive
+__device__ __forceinline__ void rf_bucket_hit(const TraceArgs &A, int orig, int64_t r, RfCoeffs c)
+{
+    if (!(c.op * c.G < 0.9999f)) c.dalpha = 0.f;      // clamped alpha: no gradient to opacity / geometry
+    if (c.dalpha == 0.f && c.dcol[0] == 0.f && c.dcol[1] == 0.f && c.dcol[2] == 0.f) return;
+    const uint32_t slot = __ldg(A.gb.prim_offsets + orig) + atomicAdd(A.gb.cursor + orig, 1u);
+    A.gb.state[slot] = make_float4(c.dcol[0], c.dcol[1], c.dcol[2], c.dalpha);
+    A.gb.ray[slot] = (uint32_t)r;
 }
 
 // one tomography interaction of the adjoint; returns T.  L stays state_in until the ray escapes (tomo:92-101).
@@ -1304,14 +1451,28 @@ __device__ __forceinline__ float tomo_adjoint_hit(const DevScene &S, const Trace
 #ifndef VP_REPLAY_BLOCKS
 #define VP_REPLAY_BLOCKS 8   // the replay adjoint uses no shared memory; bound by reduction throughput, not occupancy
 #endif
-template <int INTEG, int KERNEL, int D, bool REPLAY, bool TILE>
-__global__ void __launch_bounds__(TRACE_THREADS, REPLAY ? VP_REPLAY_BLOCKS : VP_MIN_BLOCKS) k_trace_adjoint(DevScene S, vp_params P, TraceArgs A)
+// Where the adjoint takes a ray's hit sequence from, and where the gradient of a hit goes
+enum { ADJ_WALK = 0,        // re-trace like the primal, scatter with vector reductions
+       ADJ_REPLAY_DENSE,    // replay a dense [cap, R] record, scatter
+       ADJ_REPLAY_ROWS,     // replay a compressed-row record, scatter            (volprim_tomography)
+       ADJ_REPLAY_BUCKET }; // replay a compressed-row record, per-hit coefficients to the primitive's bucket (volprim_rf)
+
+__device__ __forceinline__ bool record_usable(const GatherBuf &gb)
 {
+    return !gb.total || (gb.total[0] <= gb.capacity && gb.total[1] == 0);
+}
+
+template <int INTEG, int KERNEL, int D, int MODE, bool TILE>
+__global__ void __launch_bounds__(TRACE_THREADS, MODE != ADJ_WALK ? VP_REPLAY_BLOCKS : VP_MIN_BLOCKS) k_trace_adjoint(DevScene S, vp_params P, TraceArgs A)
+{
+    constexpr bool REPLAY = MODE != ADJ_WALK;
     extern __shared__ float4 smem_raw[];
     int *s_id = reinterpret_cast<int *>(smem_raw) + threadIdx.x;
     float *s_t = reinterpret_cast<float *>(smem_raw) + CAND_CAP * TRACE_THREADS + threadIdx.x;
     const int64_t t = (int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x;
     Counters cn = { 0, 0, 0, 0, 0, 0 };
+    if constexpr (MODE == ADJ_REPLAY_ROWS || MODE == ADJ_REPLAY_BUCKET)
+        if (!record_usable(A.gb)) return;            // truncated record: the caller re-traces (see vp_hit_record)
     const bool in_range = t < A.R;
     const int64_t r = in_range ? ray_index(t, P.image_width, P.image_height) : 0;
     float g[3] = { 0.f, 0.f, 0.f };
@@ -1321,9 +1482,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, REPLAY ? VP_REPLAY_BLOCKS : VP_
     float maxt = FLT_MAX;
     float L[3] = { 0.f, 0.f, 0.f };
     if (alive) {
-        o = make_float3(A.o[3 * r], A.o[3 * r + 1], A.o[3 * r + 2]);
-        d = make_float3(A.d[3 * r], A.d[3 * r + 1], A.d[3 * r + 2]);
-        if (A.maxt) maxt = A.maxt[r];
+        load_ray(A.src, r, o, d, maxt);
         L[0] = A.state_in[3 * r]; L[1] = A.state_in[3 * r + 1]; L[2] = A.state_in[3 * r + 2];
     }
     float3 o0 = o;
@@ -1337,9 +1496,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, REPLAY ? VP_REPLAY_BLOCKS : VP_
 
     auto interact = [&](int pos, float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is) -> bool {
         float T;
-        if constexpr (INTEG == VP_INTEGRATOR_RF)
-            T = rf_adjoint_hit<KERNEL, D>(S, A, pos, o, d, g0, g1, g2, Rm, is, beta, g, L, Y);
-        else
+        if constexpr (INTEG == VP_INTEGRATOR_RF) {
+            const RfCoeffs c = rf_adjoint_coeffs<KERNEL, D>(S, pos, o, d, g0, g1, Rm, is, beta, g, L, Y);
+            if constexpr (MODE == ADJ_REPLAY_BUCKET) rf_bucket_hit(A, __float_as_int(g1.w), r, c);
+            else rf_scatter_hit<KERNEL, D>(A, g0, g1, g2, Rm, c, Y);
+            T = c.T;
+        } else
             T = tomo_adjoint_hit<KERNEL>(S, A, o, d, g0, g1, g2, Rm, is, g, L);
         beta *= T;
         o.x = fmaf(d.x, P.eps_advance, fmaf(d.x, is.tn, o.x));
@@ -1354,17 +1516,30 @@ __global__ void __launch_bounds__(TRACE_THREADS, REPLAY ? VP_REPLAY_BLOCKS : VP_
 
     if constexpr (REPLAY) {
         if (alive) {
-            uint32_t n = A.rec_counts[r];
-            if (n > (uint32_t)A.cap) n = (uint32_t)A.cap;
+            // this ray's list: element k at list[k * stride]
+            const int32_t *list;
+            int64_t stride;
+            uint32_t n;
+            if constexpr (MODE == ADJ_REPLAY_DENSE) {
+                list = A.rec_ids + r * A.rs;
+                stride = A.hs;
+                n = A.rec_counts[r];
+                if (n > (uint32_t)A.cap) n = (uint32_t)A.cap;
+            } else {
+                const int64_t b = A.rec_offsets[r];
+                list = A.rec_ids + b;
+                stride = 1;
+                n = (uint32_t)(A.rec_offsets[r + 1] - b);
+            }
             // software pipeline: the id -> position -> records chain of hit k+1 is started during hit k
-            int orig_next = n > 0 ? A.rec_ids[r * A.rs] : -1;
+            int orig_next = n > 0 ? list[0] : -1;
             int pos_next = orig_next >= 0 ? __ldg(S.inv_perm + orig_next) : 0;
             if (orig_next >= 0) prefetch_prim(S, pos_next);
             for (uint32_t k = 0; k < n; ++k) {
                 const int orig = orig_next;
                 if (orig < 0) break;
                 const int pos = pos_next;
-                orig_next = (k + 1 < n) ? A.rec_ids[r * A.rs + (k + 1) * A.hs] : -1;
+                orig_next = (k + 1 < n) ? list[(k + 1) * stride] : -1;
                 pos_next = orig_next >= 0 ? __ldg(S.inv_perm + orig_next) : 0;
                 if (orig_next >= 0) prefetch_prim(S, pos_next);
                 float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
@@ -1381,35 +1556,180 @@ __global__ void __launch_bounds__(TRACE_THREADS, REPLAY ? VP_REPLAY_BLOCKS : VP_
     flush_counters(cn, A.stats);
 }
 
-__global__ void k_raygen(vp_camera cam, int spp, const float *__restrict__ jitter, float *__restrict__ ro,
-                         float *__restrict__ rd, float *__restrict__ rmaxt)
+// ---- gather adjoint, primitive-major pass ---------------------------------------------------------------------------
+// One warp per primitive (original numbering, so that consecutive warps stream consecutive buckets and gradient rows).
+// The lanes stride over the primitive's bucket; every lane re-evaluates its hits from (ray, primitive, per-hit
+// coefficients) and keeps the sums in registers: C colour-coefficient gradients + 16 geometry sums (opacity, dw (3),
+// w.dw (3), v (x) dw (9); the chain to centre / scale / quaternion is linear in them and applied once).  A butterfly
+// reduce-scatter (NV - NV/32 shuffles for NV values) leaves NV/32 finished sums per lane, which are ADDED to the caller's
+// buffers with plain coalesced read-modify-writes: one write per gradient float and launch, no reductions in L2.
+struct GatherArgs {
+    RaySrc src;
+    const float *data10, *attr;     // the primitives in the reference layouts (context copies, original order)
+    GatherBuf gb;
+    int64_t p_begin, p_end;
+    float *g_data, *g_attr, *g_sh;
+};
+
+template <int KERNEL, int D>
+__global__ void __launch_bounds__(128, 4) k_adjoint_gather(GatherArgs A)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t total = (int64_t)cam.width * cam.height * spp;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NB = (D >= 0) ? (D + 1) * (D + 1) : 0;
+    constexpr int C = 3 * NB;
+    constexpr int NV = (C + 16 <= 32) ? 32 : 64;    // sums per primitive, padded to a multiple of the warp size
+    constexpr int M = NV / 32;                      // finished sums per lane
+    static_assert(C + 16 <= 64, "SH degree 3 at most");
+    const int lane = threadIdx.x & 31;
+    const int64_t p = A.p_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (p >= A.p_end || !record_usable(A.gb)) return;
+    const uint32_t cnt = A.gb.cursor[p];
+    if (cnt == 0) return;
+    const uint32_t base = __ldg(A.gb.prim_offsets + p);
+    const float *rec = A.data10 + 10 * p;
+    const float4 g0 = make_float4(__ldg(rec), __ldg(rec + 1), __ldg(rec + 2), A.attr ? __ldg(A.attr + p) : 1.f);
+    const float4 g1 = make_float4(__ldg(rec + 3), __ldg(rec + 4), __ldg(rec + 5), 0.f);
+    const float4 g2 = make_float4(__ldg(rec + 6), __ldg(rec + 7), __ldg(rec + 8), __ldg(rec + 9));
+    const Mat3 Rm = vp_quat_to_matrix_rn(g2);
+    float acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.f;
+
+    // one entry ahead: the bucket entry of the next round is in flight while this one is evaluated
+    uint32_t i = lane;
+    float4 st_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t ray_next = 0;
+    if (i < cnt) { st_next = __ldcs(A.gb.state + base + i); ray_next = __ldcs(A.gb.ray + base + i); }
+    while (i < cnt) {
+        const float4 st = st_next;
+        const uint32_t r = ray_next;
+        i += 32;
+        if (i < cnt) { st_next = __ldcs(A.gb.state + base + i); ray_next = __ldcs(A.gb.ray + base + i); }
+        float3 o, d;
+        float maxt;
+        load_ray(A.src, r, o, d, maxt);
+        if constexpr (D >= 0) {
+            if (st.x != 0.f || st.y != 0.f || st.z != 0.f) {
+                float Y[NB > 0 ? NB : 1];
+                sh_basis<(D >= 0 ? D : 0)>(d, Y);
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    acc[3 * j + 0] = fmaf(Y[j], st.x, acc[3 * j + 0]);
+                    acc[3 * j + 1] = fmaf(Y[j], st.y, acc[3 * j + 1]);
+                    acc[3 * j + 2] = fmaf(Y[j], st.z, acc[3 * j + 2]);
+                }
+            }
+        }
+        if (st.w != 0.f) {
+            Isect is;
+            is.valid = true; is.tn = is.tf = 0.f;
+            is.rd = vp_rot_t_mul_rn(Rm, d);
+            is.ro = vp_rot_t_mul_rn(Rm, make_float3(o.x - g0.x, o.y - g0.y, o.z - g0.z));
+            const RfEval e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
+            acc[C] = fmaf(st.w, e.G, acc[C]);                       // d opacity
+            float3 v, w;
+            float dw[3];
+            if (rf_geo_terms<KERNEL>(g0, g1, Rm, e.pp, e.G, e.op, st.w, v, w, dw)) {
+                acc[C + 1] += dw[0]; acc[C + 2] += dw[1]; acc[C + 3] += dw[2];
+                acc[C + 4] = fmaf(w.x, dw[0], acc[C + 4]);
+                acc[C + 5] = fmaf(w.y, dw[1], acc[C + 5]);
+                acc[C + 6] = fmaf(w.z, dw[2], acc[C + 6]);
+                const float va[3] = { v.x, v.y, v.z };
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) acc[C + 7 + 3 * a + b] = fmaf(va[a], dw[b], acc[C + 7 + 3 * a + b]);
+            }
+        }
+    }
+    // butterfly reduce-scatter: after the step with lane distance s, a lane holds the partial sums of the half of the
+    // index range selected by its bit s; in the end lane l owns indices M * l .. M * l + M - 1
+#pragma unroll
+    for (int half = NV / 2, sft = 16; sft >= 1; half >>= 1, sft >>= 1) {
+        const bool up = (lane & sft) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const float keep = up ? acc[k + half] : acc[k];
+            const float send = up ? acc[k] : acc[k + half];
+            acc[k] = keep + __shfl_xor_sync(FULL, send, sft);
+        }
+    }
+    // colour coefficients: coalesced read-modify-write
+    if constexpr (C > 0) {
+        if (A.g_sh) {
+            float *dst = A.g_sh + (size_t)p * C;
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                const int idx = M * lane + k;
+                if (idx < C) dst[idx] += acc[k];
+            }
+        }
+    }
+    // geometry sums -> lane 0
+    float gs[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) gs[j] = __shfl_sync(FULL, acc[(C + j) % M], (C + j) / M);
+    if (lane == 0) {
+        A.g_attr[p] += gs[0];
+        float g10[10];
+        float dR[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            g10[a] = -(Rm.m[a][0] * gs[1] + Rm.m[a][1] * gs[2] + Rm.m[a][2] * gs[3]);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) dR[a][b] = gs[7 + 3 * a + b];
+        }
+        g10[3] = -gs[4] / g1.x;
+        g10[4] = -gs[5] / g1.y;
+        g10[5] = -gs[6] / g1.z;
+        float gq[4];
+        chain_dR_to_quat(g2, dR, gq);
+        g10[6] = gq[0]; g10[7] = gq[1]; g10[8] = gq[2]; g10[9] = gq[3];
+        float *dst = A.g_data + 10 * p;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) dst[k] += g10[k];
+    }
+}
+
+// ---- hit records: dense hit-major scratch -> compressed rows ----------------------------------------------------------
+// per-ray entry counts of a band (clamped at the record's per-ray cap) + number of rays whose list was cut
+__global__ void k_record_counts(const uint32_t *__restrict__ nhits, int64_t n, int32_t cap, uint32_t *__restrict__ counts,
+                                int64_t *__restrict__ total)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool cut = false;
+    if (r < n) {
+        const uint32_t h = nhits[r];
+        cut = h > (uint32_t)cap;
+        counts[r] = cut ? (uint32_t)cap : h;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, cut);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)(total + 1), (unsigned long long)__popc(m));
+}
+
+// one thread per ray: its column of the dense block goes to ids[offset ..).  Reads are coalesced across the warp
+// (same hit index, neighbouring rays); each thread writes its own contiguous row.
+__global__ void k_compact_hits(const int32_t *__restrict__ dense, int64_t n, const uint32_t *__restrict__ counts,
+                               const int64_t *__restrict__ offsets, int32_t *__restrict__ ids, int64_t capacity)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t c = counts[r];
+    const int64_t off = offsets[r];
+    if (off + c > capacity) return;                  // does not fit: total[0] tells the caller
+    for (uint32_t k = 0; k < c; ++k) ids[off + k] = dense[(int64_t)k * n + r];
+}
+
+__global__ void k_raygen(RaySrc S, int64_t total, float *__restrict__ ro, float *__restrict__ rd, float *__restrict__ rmaxt)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    int64_t pix = i / spp;
-    int x = (int)(pix % cam.width), y = (int)(pix / cam.width);
-    float jx = jitter ? jitter[2 * i] : 0.5f, jy = jitter ? jitter[2 * i + 1] : 0.5f;
-    float u = ((float)x + jx) / (float)cam.width, v = ((float)y + jy) / (float)cam.height;
-    float tan_half = tanf(cam.fov_x_deg * 0.5f * 0.017453292519943295f);
-    float aspect = (float)cam.width / (float)cam.height;
-    // Mitsuba perspective sensor: +z forward, +x to the LEFT of the image, +y up
-    float lx = (1.f - 2.f * u + 2.f * cam.cx) * tan_half;
-    float ly = (1.f - 2.f * v + 2.f * cam.cy) * tan_half / aspect;
-    float inv_n = rsqrtf(lx * lx + ly * ly + 1.f);
-    float3 dl = make_float3(lx * inv_n, ly * inv_n, inv_n);
-    const float *m = cam.to_world;
-    float3 dw = make_float3(m[0] * dl.x + m[1] * dl.y + m[2] * dl.z, m[4] * dl.x + m[5] * dl.y + m[6] * dl.z,
-                            m[8] * dl.x + m[9] * dl.y + m[10] * dl.z);
-    float inv_z = 1.f / dl.z;
-    float near_t = cam.near_clip * inv_z, far_t = cam.far_clip * inv_z;
-    ro[3 * i] = fmaf(dw.x, near_t, m[3]);
-    ro[3 * i + 1] = fmaf(dw.y, near_t, m[7]);
-    ro[3 * i + 2] = fmaf(dw.z, near_t, m[11]);
-    rd[3 * i] = dw.x;
-    rd[3 * i + 1] = dw.y;
-    rd[3 * i + 2] = dw.z;
-    if (rmaxt) rmaxt[i] = far_t - near_t;
+    float3 o, d;
+    float maxt;
+    camera_ray(S, i, o, d, maxt);
+    ro[3 * i] = o.x; ro[3 * i + 1] = o.y; ro[3 * i + 2] = o.z;
+    rd[3 * i] = d.x; rd[3 * i + 1] = d.y; rd[3 * i + 2] = d.z;
+    if (rmaxt) rmaxt[i] = maxt;
 }
 
 template <int INTEG, int KERNEL, int D>
@@ -1425,19 +1745,37 @@ template <int INTEG, int KERNEL, int D>
 void launch_adjoint(const DevScene &S, const vp_params &P, const TraceArgs &A, cudaStream_t st)
 {
     int64_t blocks = (A.R + TRACE_THREADS - 1) / TRACE_THREADS;
-    if (A.rec_ids) k_trace_adjoint<INTEG, KERNEL, D, true, false><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
-    else if (P.image_width > 0) k_trace_adjoint<INTEG, KERNEL, D, false, true><<<(unsigned)blocks, TRACE_THREADS, TILE_SMEM, st>>>(S, P, A);
-    else k_trace_adjoint<INTEG, KERNEL, D, false, false><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
+    if (A.rec_offsets) {
+        if constexpr (INTEG == VP_INTEGRATOR_RF)
+            k_trace_adjoint<INTEG, KERNEL, D, ADJ_REPLAY_BUCKET, false><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
+        else
+            k_trace_adjoint<INTEG, KERNEL, D, ADJ_REPLAY_ROWS, false><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
+    } else if (A.rec_ids) k_trace_adjoint<INTEG, KERNEL, D, ADJ_REPLAY_DENSE, false><<<(unsigned)blocks, TRACE_THREADS, 0, st>>>(S, P, A);
+    else if (P.image_width > 0) k_trace_adjoint<INTEG, KERNEL, D, ADJ_WALK, true><<<(unsigned)blocks, TRACE_THREADS, TILE_SMEM, st>>>(S, P, A);
+    else k_trace_adjoint<INTEG, KERNEL, D, ADJ_WALK, false><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
 }
 
-template <bool FWD>
-int dispatch(vp_ctx *ctx, const DevScene &S, const vp_params &P, const TraceArgs &A, cudaStream_t st)
+template <int INTEG, int KERNEL, int D>
+void launch_gather(const GatherArgs &G, cudaStream_t st)
 {
-#define VP_LAUNCH(I, K, D)                                   \
-    do {                                                     \
-        if (FWD) launch_forward<I, K, D>(S, P, A, st);       \
-        else launch_adjoint<I, K, D>(S, P, A, st);           \
-        return VP_OK;                                        \
+    if constexpr (INTEG == VP_INTEGRATOR_RF) {
+        const int64_t warps = G.p_end - G.p_begin;
+        if (warps <= 0) return;
+        const int64_t blocks = (warps * 32 + 127) / 128;
+        k_adjoint_gather<KERNEL, D><<<(unsigned)blocks, 128, 0, st>>>(G);
+    }
+}
+
+// WHAT: 0 = forward, 1 = adjoint (ray-major), 2 = gather (primitive-major pass of the rf adjoint)
+template <int WHAT>
+int dispatch(vp_ctx *ctx, const DevScene &S, const vp_params &P, const TraceArgs &A, const GatherArgs *G, cudaStream_t st)
+{
+#define VP_LAUNCH(I, K, D)                                        \
+    do {                                                          \
+        if (WHAT == 0) launch_forward<I, K, D>(S, P, A, st);      \
+        else if (WHAT == 1) launch_adjoint<I, K, D>(S, P, A, st); \
+        else launch_gather<I, K, D>(*G, st);                      \
+        return VP_OK;                                             \
     } while (0)
     const bool gauss = P.kernel == VP_KERNEL_GAUSSIAN;
     if (P.integrator == VP_INTEGRATOR_TOMO) {
@@ -1474,6 +1812,67 @@ int check_common(vp_ctx *ctx, const vp_params *p, int64_t R, const char *who)
     return VP_OK;
 }
 
+// gradient buffers take 64-bit (record) and 128-bit (colour coefficient) vector reductions in the scatter formulation
+int check_grad_alignment(vp_ctx *ctx, const float *g_data, const float *g_sh, int sh_floats, const char *who)
+{
+    if ((uintptr_t)g_data % 8) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": g_data10 must be 8-byte aligned");
+    if (g_sh && sh_floats % 4 == 0 && (uintptr_t)g_sh % 16)
+        return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": g_sh must be 16-byte aligned");
+    return VP_OK;
+}
+
+// Resolve a vp_ray_source into the kernels' RaySrc; *image_w / *image_h receive the tile-walker hint of a sensor.
+int make_ray_src(vp_ctx *ctx, const vp_ray_source *rs, int64_t R, RaySrc &out, int &image_w, int &image_h, const char *who)
+{
+    if (!rs) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": rays is NULL");
+    out = RaySrc{};
+    image_w = image_h = 0;
+    if (rs->camera) {
+        const vp_camera &c = *rs->camera;
+        if (c.width <= 0 || c.height <= 0 || rs->spp <= 0) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": bad film size or spp");
+        const int rows = rs->row_count > 0 ? rs->row_count : c.height - rs->row_begin;
+        if (rs->row_begin < 0 || rows <= 0 || rs->row_begin + rows > c.height)
+            return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": row band outside the film");
+        if (R != (int64_t)c.width * rows * rs->spp)
+            return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": n_rays must equal width * rows * spp of the sensor");
+        out.cam = c;
+        out.tan_half = (float)std::tan((double)c.fov_x_deg * 0.5 * 0.017453292519943295);
+        out.has_cam = 1;
+        out.spp = rs->spp;
+        out.jitter = rs->jitter;
+        out.index_base = (int64_t)rs->row_begin * c.width * rs->spp;
+        if (((int64_t)c.width * rs->spp) % 8 == 0 && rows % 4 == 0) { image_w = c.width * rs->spp; image_h = rows; }
+    } else {
+        if (R > 0 && (!rs->ray_o || !rs->ray_d)) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": ray_o and ray_d (or a camera) are required");
+        out.o = rs->ray_o; out.d = rs->ray_d; out.maxt = rs->ray_maxt;
+        out.spp = 1;
+    }
+    return VP_OK;
+}
+
+// the part of a ray source that belongs to rays [first, first + n) of the call
+RaySrc slice_ray_src(const RaySrc &s, int64_t first)
+{
+    RaySrc o = s;
+    if (s.has_cam) {
+        o.index_base = s.index_base + first;
+        if (s.jitter) o.jitter = s.jitter + 2 * first;
+    } else {
+        o.o = s.o + 3 * first; o.d = s.d + 3 * first;
+        if (s.maxt) o.maxt = s.maxt + first;
+    }
+    return o;
+}
+
+int check_record(vp_ctx *ctx, const vp_hit_record *rec, const char *who)
+{
+    if (!rec->ray_offsets || !rec->ids || !rec->prim_offsets || !rec->total)
+        return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record arrays (ray_offsets, ids, prim_offsets, total) are required");
+    if (rec->capacity <= 0 || rec->capacity >= (1ll << 32) || rec->id_cap <= 0)
+        return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record needs 0 < capacity < 2^32 and id_cap > 0");
+    return VP_OK;
+}
+
 }  // namespace
 
 int vp_trace_forward_impl(vp_ctx *ctx, const vp_params *p, int64_t R, const float *o, const float *d, const float *maxt,
@@ -1489,10 +1888,11 @@ int vp_trace_forward_impl(vp_ctx *ctx, const vp_params *p, int64_t R, const floa
     VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->stats.ptr, 0, sizeof(vp_stats), st));
     DevScene S = vp_dev_scene(ctx);
     TraceArgs A = {};
-    A.R = R; A.o = o; A.d = d; A.maxt = maxt; A.rgb = rgb; A.T = T; A.nhits = nhits;
+    A.R = R; A.src.o = o; A.src.d = d; A.src.maxt = maxt; A.src.spp = 1;
+    A.rgb = rgb; A.T = T; A.nhits = nhits;
     A.ids = ids; A.cap = ids ? cap : 0; A.rs = rs; A.hs = hs;
     A.stats = (vp_stats *)ctx->stats.ptr;
-    rc = dispatch<true>(ctx, S, *p, A, st);
+    rc = dispatch<0>(ctx, S, *p, A, nullptr, st);
     if (rc) return rc;
     VP_CUDA_CHECK(ctx, cudaGetLastError());
     return VP_OK;
@@ -1511,15 +1911,17 @@ int vp_trace_adjoint_impl(vp_ctx *ctx, const vp_params *p, int64_t R, const floa
     if (ids && (!counts || cap <= 0)) return vp_fail(ctx, VP_E_INVALID, "vp_trace_adjoint: hit_ids needs hit_counts and id_cap > 0");
     if (p->integrator == VP_INTEGRATOR_RF && ctx->sh_floats > 0 && !g_sh)
         return vp_fail(ctx, VP_E_INVALID, "vp_trace_adjoint: g_sh is required when the primitives carry sh_coeffs");
+    if ((rc = check_grad_alignment(ctx, g_data, g_sh, ctx->sh_floats, "vp_trace_adjoint"))) return rc;
     if ((rc = vp_ensure(ctx, ctx->stats, sizeof(vp_stats)))) return rc;
     VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->stats.ptr, 0, sizeof(vp_stats), st));
     DevScene S = vp_dev_scene(ctx);
     TraceArgs A = {};
-    A.R = R; A.o = o; A.d = d; A.maxt = maxt; A.dL = dL; A.state_in = state_in;
+    A.R = R; A.src.o = o; A.src.d = d; A.src.maxt = maxt; A.src.spp = 1;
+    A.dL = dL; A.state_in = state_in;
     A.rec_ids = ids; A.rec_counts = counts; A.cap = cap; A.rs = rs; A.hs = hs;
     A.g_data = g_data; A.g_attr = g_attr; A.g_sh = g_sh;
     A.stats = (vp_stats *)ctx->stats.ptr;
-    rc = dispatch<false>(ctx, S, *p, A, st);
+    rc = dispatch<1>(ctx, S, *p, A, nullptr, st);
     if (rc) return rc;
     VP_CUDA_CHECK(ctx, cudaGetLastError());
     return VP_OK;
@@ -1531,7 +1933,197 @@ int vp_raygen_impl(vp_ctx *ctx, const vp_camera *cam, int32_t spp, const float *
     if (!cam || !o || !d) return vp_fail(ctx, VP_E_INVALID, "vp_raygen_perspective: camera, ray_o and ray_d are required");
     if (cam->width <= 0 || cam->height <= 0 || spp <= 0) return vp_fail(ctx, VP_E_INVALID, "vp_raygen_perspective: bad film size or spp");
     int64_t total = (int64_t)cam->width * cam->height * spp;
-    k_raygen<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(*cam, spp, jitter, o, d, maxt);
+    vp_ray_source rs = {};
+    rs.camera = cam; rs.spp = spp; rs.jitter = jitter;
+    RaySrc src;
+    int iw, ih;
+    int rc = make_ray_src(ctx, &rs, total, src, iw, ih, "vp_raygen_perspective");
+    if (rc) return rc;
+    k_raygen<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, total, o, d, maxt);
+    VP_CUDA_CHECK(ctx, cudaGetLastError());
+    return VP_OK;
+}
+
+// ---- sensor-fused / record-replay entry points -------------------------------------------------------------------------
+int vp_render_forward_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_source *rays, int64_t R, float *rgb, float *T,
+                           uint32_t *nhits, const vp_hit_record *rec, cudaStream_t st)
+{
+    if (!p_in) return vp_fail(ctx, VP_E_INVALID, "vp_render_forward: params is NULL");
+    vp_params P = *p_in;
+    RaySrc src;
+    int iw, ih;
+    int rc = make_ray_src(ctx, rays, R, src, iw, ih, "vp_render_forward");
+    if (rc) return rc;
+    if (src.has_cam) { P.image_width = iw; P.image_height = ih; }
+    if ((rc = check_common(ctx, &P, R, "vp_render_forward"))) return rc;
+    if (rec && (rc = check_record(ctx, rec, "vp_render_forward"))) return rc;
+    if (R > 0 && !rgb) return vp_fail(ctx, VP_E_INVALID, "vp_render_forward: out_rgb is required");
+    if ((rc = vp_ensure(ctx, ctx->stats, sizeof(vp_stats)))) return rc;
+    VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->stats.ptr, 0, sizeof(vp_stats), st));
+    DevScene S = vp_dev_scene(ctx);
+    TraceArgs A = {};
+    A.rgb = rgb; A.T = T; A.nhits = nhits;
+    A.stats = (vp_stats *)ctx->stats.ptr;
+    if (!rec) {
+        if (R == 0) return VP_OK;
+        A.R = R; A.src = src;
+        if ((rc = dispatch<0>(ctx, S, P, A, nullptr, st))) return rc;
+        VP_CUDA_CHECK(ctx, cudaGetLastError());
+        return VP_OK;
+    }
+    // ---- recording: row bands bound the dense hit-major scratch ----
+    const int64_t n = ctx->n;
+    VP_CUDA_CHECK(ctx, cudaMemsetAsync(rec->total, 0, 2 * sizeof(int64_t), st));
+    VP_CUDA_CHECK(ctx, cudaMemsetAsync(rec->prim_offsets, 0, sizeof(uint32_t) * (size_t)(n + 1), st));
+    if (R == 0) {
+        VP_CUDA_CHECK(ctx, cudaMemsetAsync(rec->ray_offsets, 0, sizeof(int64_t), st));
+        return VP_OK;
+    }
+    const int cap = rec->id_cap;
+    int64_t band;                                     // rays per band
+    const int64_t fit = ctx->record_scratch_bytes / ((int64_t)cap * 4);
+    const int64_t per_image = P.image_width > 0 ? (int64_t)P.image_width * P.image_height : 0;
+    int64_t rows_per_band = 0;
+    if (per_image > 0) {
+        rows_per_band = (fit / P.image_width) & ~3ll;
+        if (rows_per_band < 4) rows_per_band = 4;
+        if (rows_per_band > P.image_height) rows_per_band = P.image_height;
+        band = rows_per_band * P.image_width;
+    } else {
+        band = fit & ~(int64_t)(TRACE_THREADS - 1);
+        if (band < TRACE_THREADS) band = TRACE_THREADS;
+        if (band > R) band = R;
+    }
+    if ((rc = vp_ensure(ctx, ctx->rec_dense, sizeof(int32_t) * (size_t)cap * (size_t)band))) return rc;
+    if ((rc = vp_ensure(ctx, ctx->rec_counts, sizeof(uint32_t) * (size_t)band))) return rc;
+    if ((rc = vp_ensure(ctx, ctx->scan_tmp, sizeof(uint64_t) * (size_t)(vpscan::n_tiles(band > n ? band : n) + 1)))) return rc;
+    uint32_t *nh_all = nhits;
+    if (!nh_all) {
+        if ((rc = vp_ensure(ctx, ctx->rec_nhits, sizeof(uint32_t) * (size_t)R))) return rc;
+        nh_all = (uint32_t *)ctx->rec_nhits.ptr;
+    }
+    int64_t first = 0;
+    while (first < R) {
+        int64_t cnt = band;
+        vp_params Pb = P;
+        if (per_image > 0) {
+            const int64_t in_img = first % per_image;               // bands never straddle two images
+            const int64_t rows_left = (per_image - in_img) / P.image_width;
+            const int64_t rows = rows_left < rows_per_band ? rows_left : rows_per_band;
+            cnt = rows * P.image_width;
+            Pb.image_height = (int32_t)rows;
+        } else if (first + cnt > R) cnt = R - first;
+        TraceArgs B = A;
+        B.R = cnt;
+        B.src = slice_ray_src(src, first);
+        B.rgb = rgb + 3 * first;
+        B.T = T ? T + first : nullptr;
+        B.nhits = nh_all + first;
+        B.ids = (int32_t *)ctx->rec_dense.ptr; B.cap = cap; B.rs = 1; B.hs = cnt;
+        B.prim_counts = rec->prim_offsets;
+        if ((rc = dispatch<0>(ctx, S, Pb, B, nullptr, st))) return rc;
+        const unsigned blocks = (unsigned)((cnt + 255) / 256);
+        k_record_counts<<<blocks, 256, 0, st>>>(B.nhits, cnt, cap, (uint32_t *)ctx->rec_counts.ptr, rec->total);
+        vpscan::exclusive_scan<unsigned long long>((const uint32_t *)ctx->rec_counts.ptr, cnt,
+                                                   (unsigned long long *)rec->ray_offsets + first,
+                                                   (unsigned long long *)ctx->scan_tmp.ptr, (unsigned long long *)rec->total,
+                                                   (unsigned long long *)rec->ray_offsets + first + cnt, st);
+        k_compact_hits<<<blocks, 256, 0, st>>>((const int32_t *)ctx->rec_dense.ptr, cnt, (const uint32_t *)ctx->rec_counts.ptr,
+                                               rec->ray_offsets + first, rec->ids, rec->capacity);
+        first += cnt;
+    }
+    // per-primitive hit counts -> bucket offsets (in place; [n] receives the total)
+    vpscan::exclusive_scan<uint32_t>(rec->prim_offsets, n, rec->prim_offsets, (uint32_t *)ctx->scan_tmp.ptr, nullptr,
+                                     rec->prim_offsets + n, st);
+    VP_CUDA_CHECK(ctx, cudaGetLastError());
+    return VP_OK;
+}
+
+namespace {
+int adjoint_common(vp_ctx *ctx, const vp_params *p_in, const vp_ray_source *rays, int64_t R, const vp_hit_record *rec,
+                   float *g_data, float *g_attr, float *g_sh, const char *who, vp_params &P, RaySrc &src)
+{
+    if (!p_in) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": params is NULL");
+    P = *p_in;
+    int iw, ih;
+    int rc = make_ray_src(ctx, rays, R, src, iw, ih, who);
+    if (rc) return rc;
+    P.image_width = P.image_height = 0;       // the replay passes index rays linearly
+    if ((rc = check_common(ctx, &P, R, who))) return rc;
+    if (!rec) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": a hit record is required (vp_trace_adjoint re-traces)");
+    if ((rc = check_record(ctx, rec, who))) return rc;
+    if (!g_data || !g_attr) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": g_data10 and g_attr are required");
+    if (P.integrator == VP_INTEGRATOR_RF && ctx->sh_floats > 0 && !g_sh)
+        return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": g_sh is required when the primitives carry sh_coeffs");
+    return check_grad_alignment(ctx, g_data, g_sh, ctx->sh_floats, who);
+}
+
+GatherBuf gather_buf(vp_ctx *ctx, const vp_hit_record *rec)
+{
+    GatherBuf gb;
+    gb.prim_offsets = rec->prim_offsets;
+    gb.cursor = (uint32_t *)ctx->adj_cursor.ptr;
+    gb.state = (float4 *)ctx->adj_state.ptr;
+    gb.ray = (uint32_t *)ctx->adj_ray.ptr;
+    gb.total = rec->total;
+    gb.capacity = rec->capacity;
+    return gb;
+}
+}  // namespace
+
+int vp_adjoint_begin_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_source *rays, int64_t R, const float *dL,
+                          const float *state_in, const vp_hit_record *rec, float *g_data, float *g_attr, float *g_sh,
+                          cudaStream_t st)
+{
+    vp_params P;
+    RaySrc src;
+    int rc = adjoint_common(ctx, p_in, rays, R, rec, g_data, g_attr, g_sh, "vp_adjoint_begin", P, src);
+    if (rc) return rc;
+    if (R > 0 && (!dL || !state_in)) return vp_fail(ctx, VP_E_INVALID, "vp_adjoint_begin: d_L and state_in are required");
+    if (R >= (1ll << 32)) return vp_fail(ctx, VP_E_INVALID, "vp_adjoint_begin: more than 2^32 rays per call are not supported");
+    if ((rc = vp_ensure(ctx, ctx->stats, sizeof(vp_stats)))) return rc;
+    VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->stats.ptr, 0, sizeof(vp_stats), st));
+    DevScene S = vp_dev_scene(ctx);
+    TraceArgs A = {};
+    A.R = R; A.src = src; A.dL = dL; A.state_in = state_in;
+    A.rec_ids = rec->ids; A.rec_offsets = rec->ray_offsets;
+    A.g_data = g_data; A.g_attr = g_attr; A.g_sh = g_sh;
+    A.stats = (vp_stats *)ctx->stats.ptr;
+    if (P.integrator == VP_INTEGRATOR_RF) {
+        const int64_t n = ctx->n;
+        if ((rc = vp_ensure(ctx, ctx->adj_cursor, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1)))) return rc;
+        if ((rc = vp_ensure(ctx, ctx->adj_state, sizeof(float4) * (size_t)rec->capacity))) return rc;
+        if ((rc = vp_ensure(ctx, ctx->adj_ray, sizeof(uint32_t) * (size_t)rec->capacity))) return rc;
+        VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->adj_cursor.ptr, 0, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1), st));
+    }
+    A.gb = gather_buf(ctx, rec);
+    if (R == 0) return VP_OK;
+    if ((rc = dispatch<1>(ctx, S, P, A, nullptr, st))) return rc;
+    VP_CUDA_CHECK(ctx, cudaGetLastError());
+    return VP_OK;
+}
+
+int vp_adjoint_finish_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_source *rays, int64_t R, const vp_hit_record *rec,
+                           int64_t p_begin, int64_t p_end, float *g_data, float *g_attr, float *g_sh, cudaStream_t st)
+{
+    vp_params P;
+    RaySrc src;
+    int rc = adjoint_common(ctx, p_in, rays, R, rec, g_data, g_attr, g_sh, "vp_adjoint_finish", P, src);
+    if (rc) return rc;
+    if (P.integrator != VP_INTEGRATOR_RF) return VP_OK;   // volprim_tomography scattered everything in vp_adjoint_begin
+    if (p_begin < 0 || p_end > ctx->n || p_begin > p_end) return vp_fail(ctx, VP_E_INVALID, "vp_adjoint_finish: bad primitive range");
+    if (!ctx->adj_cursor.ptr || !ctx->adj_state.ptr) return vp_fail(ctx, VP_E_STATE, "vp_adjoint_finish: call vp_adjoint_begin first");
+    if (p_begin == p_end) return VP_OK;
+    DevScene S = vp_dev_scene(ctx);
+    GatherArgs G = {};
+    G.src = src;
+    G.data10 = (const float *)ctx->raw_data.ptr;
+    G.attr = ctx->have_attr ? (const float *)ctx->raw_attr.ptr : nullptr;
+    G.gb = gather_buf(ctx, rec);
+    G.p_begin = p_begin; G.p_end = p_end;
+    G.g_data = g_data; G.g_attr = g_attr; G.g_sh = g_sh;
+    TraceArgs A = {};
+    if ((rc = dispatch<2>(ctx, S, P, A, &G, st))) return rc;
     VP_CUDA_CHECK(ctx, cudaGetLastError());
     return VP_OK;
 }

@@ -54,6 +54,11 @@ class VolprimIntegratorBase:
         env = scene.environment_radiance() if scene is not None else (0.0, 0.0, 0.0)
         p.env[0], p.env[1], p.env[2] = env
         p.image_width, p.image_height = image if image else (0, 0)
+        # Russian roulette (volprim_rf.py:39,177-183): primal pass only, PCG32 stream per ray
+        p.use_rr = int(bool(getattr(self, 'use_rr', False)))
+        p.rr_depth = int(getattr(self, 'rr_depth', 0xFFFFFFFF)) & 0xFFFFFFFF
+        p.rr_seed = int(getattr(self, 'rr_seed', 0)) & 0xFFFFFFFF
+        p.rr_skip = int(getattr(self, 'rr_skip', 0)) & 0xFFFFFFFF
         return p
 
     def _cap(self) -> int:
@@ -64,8 +69,8 @@ class VolprimIntegratorBase:
     # ---- RBIntegrator.sample ---------------------------------------------------------------------
     def sample(self, mode, scene, sampler, ray, δL=None, state_in=None, active=True, **kwargs):
         """Same contract as the reference plugins (volprim_rf.py:103-192, volprim_tomography.py:47-127):
-        returns (spectrum, valid, aovs, state_out).  `ray` carries CUDA tensors; `sampler` is unused because
-        Russian roulette is never active in this implementation (it raises at construction otherwise).
+        returns (spectrum, valid, aovs, state_out).  `ray` carries CUDA tensors; `sampler` is unused: the only
+        consumer of random numbers, Russian roulette, draws from the kernel's own PCG32 restatement (rr_seed).
         Backward mode scatters the parameter gradients into the shape's `.grad` buffers."""
         shape = get_ellipsoids_shape(scene)
         accel = shape.accel()

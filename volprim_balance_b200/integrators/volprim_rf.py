@@ -30,12 +30,14 @@ class VolumetricPrimitiveRadianceFieldIntegrator(VolprimIntegratorBase):
             raise Exception("\"rr_depth\" must be set to -1 (infinite) or a value >= 0")
         self.rr_depth = rr_depth if rr_depth != -1 else 0xFFFFFFFF
         # Russian roulette is enabled by the reference iff rr_depth >= 0 and (rr_depth < max_depth or
-        # max_depth == -1) (volprim_rf.py:39).  Every shipped configuration keeps it off; it draws from
-        # Mitsuba's sampler stream, which is third-party and unpinned, so it is refused instead of faked.
+        # max_depth == -1) (volprim_rf.py:39); every shipped configuration keeps it off.  It runs in the primal pass
+        # only (volprim_rf.py:178) and draws `sampler.next_1d()` once per loop iteration: the kernels restate
+        # Mitsuba's `independent` sampler (PCG32 stream per ray seeded by TEA(seed, ray index); third-party,
+        # unpinned).  `rr_seed` / `rr_skip` (samples a ray drew before sample(): 2 under render(), the film
+        # position) select the stream position.
         self.use_rr = rr_depth >= 0 and (rr_depth < max_depth or max_depth == -1)
-        if self.use_rr:
-            raise NotImplementedError("Russian roulette (rr_depth < max_depth) is not supported by the CUDA "
-                                      "integrator; set rr_depth >= max_depth as all reference examples do")
+        self.rr_seed = int(props.get('rr_seed', 0))
+        self.rr_skip = int(props.get('rr_skip', 0))
         self.srgb_primitives = props.get('srgb_primitives', True)
         props['kernel_full_range'] = True
         props['kernel_normalized'] = True

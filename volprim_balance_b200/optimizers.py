@@ -127,8 +127,12 @@ class BoundedAdam:
         lib = _cabi.load_library()
         val = p.detach().contiguous().clone()
         g = p.grad.detach().contiguous()
+        if g.data_ptr() % 16:      # e.g. a slice of a packed all-reduce buffer: the kernel wants 16-byte aligned rows
+            g = g.clone()
         m, v = self.state[k]
         m, v = m.contiguous(), v.contiguous()
+        if m.data_ptr() % 16 or v.data_ptr() % 16:
+            m, v = m.clone(), v.clone()
         upper, lower = self.bounds.get(k, (None, None))
         ptr = lambda t: C.c_void_p(t.data_ptr())
         with torch.cuda.device(p.device):

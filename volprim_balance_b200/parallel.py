@@ -1,8 +1,9 @@
 """Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink / NVSwitch).
 
 The path shards by RAYS: every rank holds the full primitive set and its own LBVH (replicated), and renders its
-own camera views -- or, when there are fewer views than ranks, its own band of 4-row tile strips of a view.  The
-forward pass needs no data-path collective; images are gathered to rank 0 off the critical path.  Optimisation
+own camera views (`render_views`) -- or, when there are fewer views than ranks, its own band of 4-row tile strips of
+a view (`render_tiles`: `render(..., rows=(y0, y1))` per rank + gather).  The forward pass needs no data-path
+collective; images are gathered to rank 0 off the critical path.  Optimisation
 needs exactly one exchange per step: the SUM of the per-primitive gradients, done as ONE all-reduce over a packed
 [N * (10 + 1 + C)] buffer; every rank then applies the identical optimiser step and rebuilds its own LBVH, which is
 deterministic, so the replicas stay bit-identical.
@@ -41,8 +42,21 @@ def shard_rows(height: int, rank: int = None, world_size: int = None, granule: i
     return min(s0 * granule, height), min(s1 * granule, height)
 
 
+def _padded(n: int, granule: int = 4) -> int:
+    return (n + granule - 1) // granule * granule
+
+
 def pack_gradients(grads: Dict[str, torch.Tensor], keys: Sequence[str]) -> torch.Tensor:
-    return torch.cat([grads[k].reshape(-1) for k in keys])
+    """One flat fp32 buffer; every segment starts on a 16-byte boundary (the fused optimiser kernel and the vector
+    reductions of the adjoint need aligned rows, and primitive counts are arbitrary)."""
+    some = grads[keys[0]]
+    flat = torch.zeros(sum(_padded(grads[k].numel()) for k in keys), dtype=some.dtype, device=some.device)
+    off = 0
+    for k in keys:
+        n = grads[k].numel()
+        flat[off:off + n] = grads[k].reshape(-1)
+        off += _padded(n)
+    return flat
 
 
 def unpack_gradients(flat: torch.Tensor, like: Dict[str, torch.Tensor], keys: Sequence[str]) -> Dict[str, torch.Tensor]:
@@ -50,7 +64,58 @@ def unpack_gradients(flat: torch.Tensor, like: Dict[str, torch.Tensor], keys: Se
     for k in keys:
         n = like[k].numel()
         out[k] = flat[off:off + n].reshape(like[k].shape)
-        off += n
+        off += _padded(n)
+    return out
+
+
+class GradientBucket:
+    """The primitive gradients of one rank as aligned views of ONE flat buffer: the adjoint kernels accumulate straight
+    into `data` [N*10], `attr` [N], `sh` [N*C]; the all-reduce runs over the flat buffer (no packing copy) or, chunk by
+    chunk, over the three slices of a primitive range while the next range is still being accumulated."""
+
+    def __init__(self, n: int, sh_floats: int, device):
+        self.n, self.sh_floats = n, sh_floats
+        sizes = (n * 10, n, n * sh_floats)
+        offs, off = [], 0
+        for sz in sizes:
+            offs.append(off)
+            off += _padded(sz)
+        self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=device)
+        self.data = self.flat[offs[0]:offs[0] + sizes[0]]
+        self.attr = self.flat[offs[1]:offs[1] + sizes[1]]
+        self.sh = self.flat[offs[2]:offs[2] + sizes[2]] if sh_floats else None
+
+    def tensors(self):
+        return self.data, self.attr, self.sh
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def chunk_views(self, p0: int, p1: int):
+        v = [self.data[10 * p0:10 * p1], self.attr[p0:p1]]
+        if self.sh is not None:
+            v.append(self.sh[self.sh_floats * p0:self.sh_floats * p1])
+        return v
+
+    def all_reduce(self, group=None):
+        if world()[1] > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+
+    def all_reduce_chunk(self, p0: int, p1: int, group=None):
+        """Asynchronous SUM over the slices of primitives [p0, p1); returns the work handles."""
+        if world()[1] == 1:
+            return []
+        return [dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group, async_op=True) for v in self.chunk_views(p0, p1)]
+
+
+def chunk_ranges(n: int, n_chunks: int, granule: int = 4):
+    """[p0, p1) primitive ranges of about equal size with boundaries on multiples of `granule` (aligned slices)."""
+    n_chunks = max(1, min(n_chunks, max(1, n // granule)))
+    step = _padded((n + n_chunks - 1) // n_chunks, granule)
+    out, p = [], 0
+    while p < n:
+        out.append((p, min(n, p + step)))
+        p += step
     return out
 
 
@@ -94,6 +159,31 @@ def gather_images(local: Dict[int, torch.Tensor], n_views: int, dst: int = 0, gr
         for k in range(counts[r]):
             out.append(bufs[r][k])
     return out
+
+
+def render_tiles(scene, sensor, render_fn, dst: int = 0, group=None, **kw):
+    """ONE view over all ranks (views < GPUs): every rank renders its band of 4-row tile strips with
+    `render_fn(scene, sensor=sensor, rows=(y0, y1), **kw)`; the bands are gathered on rank `dst` (NCCL gather over
+    NVLink when the process group is NCCL), which returns the assembled [H, W, 3] image; None elsewhere."""
+    rank, ws = world()
+    H = sensor.height
+    y0, y1 = shard_rows(H, rank, ws)
+    band = render_fn(scene, sensor=sensor, rows=(y0, y1), **kw) if y1 > y0 else None
+    if ws == 1:
+        return band
+    W = sensor.width
+    bands = [shard_rows(H, r, ws) for r in range(ws)]
+    max_rows = max(b - a for a, b in bands)
+    device = band.device if band is not None else (torch.device('cuda', torch.cuda.current_device())
+                                                   if dist.get_backend(group) == 'nccl' else torch.device('cpu'))
+    buf = torch.zeros((max_rows, W, 3), dtype=torch.float32, device=device)
+    if band is not None:
+        buf[:y1 - y0] = band
+    bufs = [torch.empty_like(buf) for _ in range(ws)] if rank == dst else None
+    dist.gather(buf, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([bufs[r][:b - a] for r, (a, b) in enumerate(bands) if b > a], dim=0)
 
 
 def render_views(scene, sensors: Sequence, render_fn, dst: int = 0, **kw):

@@ -2,8 +2,9 @@
 `render`.  These mirror the slice of Mitsuba's Python API the reference's callers use around the two
 integrators (examples/render_3dg_asset.py:53-77, examples/refine_3dg_dataset.py:66-189,
 examples/optimize_volume.py:132-249), with PyTorch CUDA tensors in place of Dr.Jit arrays.  No arithmetic
-of the per-ray path happens here: rays come from `vp_raygen_perspective`, radiance from
-`vp_trace_forward`, parameter gradients from `vp_trace_adjoint`.
+of the per-ray path happens here: `render()` hands the sensor to `vp_render_forward` (rays are generated inside the
+trace kernel), reconstructs the film with `vp_film_*`, and gets parameter gradients from `vp_render_adjoint`
+(replay of the primal's compressed hit records) or `vp_trace_adjoint` (re-trace).
 """
 from __future__ import annotations
 
@@ -286,6 +287,11 @@ def traverse(scene: Scene) -> SceneParameters:
 # ---------------------------------------------------------------------------------------------------
 # render
 # ---------------------------------------------------------------------------------------------------
+REUSE_PRIMAL_RECORDS = True      # False: always re-trace in the backward pass, as RBIntegrator.render_backward does
+RECORD_BUDGET_BYTES = 8 << 30    # hit records kept between the primal and the backward pass, summed over the views of a
+                                 # render() call; views beyond the budget are re-traced in the backward pass
+
+
 def _sample_positions(W, H, spp, seed, jitter, device):
     if not jitter:
         return None
@@ -294,69 +300,49 @@ def _sample_positions(W, H, spp, seed, jitter, device):
     return torch.rand((W * H * spp, 2), generator=g, device=device, dtype=torch.float32)
 
 
-def _film_weights(sensor_w, H, spp, jit, rfilter, device):
-    """Reconstruction: returns (pixel index [S,K], weight [S,K]) for the S samples; K = 1 (box / centres) or 4
-    (tent, radius 1: the 2x2 pixel centres around the sample)."""
-    S = sensor_w * H * spp
-    pix = torch.arange(sensor_w * H, device=device).repeat_interleave(spp)
-    if jit is None or rfilter == 'box':
-        return pix.reshape(S, 1), torch.ones((S, 1), device=device)
-    if rfilter not in ('tent', 'gaussian'):
-        raise Exception(f"unsupported reconstruction filter '{rfilter}'")
-    x = (pix % sensor_w).float() + jit[:, 0]
-    y = (pix // sensor_w).float() + jit[:, 1]
-    x0, y0 = torch.floor(x - 0.5), torch.floor(y - 0.5)
-    idx, wts = [], []
-    for dy in (0, 1):
-        for dx in (0, 1):
-            px, py = x0 + dx, y0 + dy
-            if rfilter == 'tent':
-                w = (1 - (x - (px + 0.5)).abs()).clamp_min(0) * (1 - (y - (py + 0.5)).abs()).clamp_min(0)
-            else:  # Mitsuba gaussian rfilter: stddev 0.5, radius 4 stddev, truncated -- approximated on the 2x2 support
-                r2 = (x - (px + 0.5)) ** 2 + (y - (py + 0.5)) ** 2
-                w = torch.exp(-r2 / (2 * 0.25))
-            ok = (px >= 0) & (px < sensor_w) & (py >= 0) & (py < H)
-            idx.append((py.clamp(0, H - 1) * sensor_w + px.clamp(0, sensor_w - 1)).long())
-            wts.append(w * ok)
-    return torch.stack(idx, 1), torch.stack(wts, 1)
+def _rfilter_id(name):
+    if name not in _cabi.RFILTERS:
+        raise Exception(f"unsupported reconstruction filter '{name}' (supported: {sorted(_cabi.RFILTERS)})")
+    return _cabi.RFILTERS[name]
 
 
-REUSE_PRIMAL_RECORDS = True   # False: always re-render the primal in the backward pass, as RBIntegrator does
+class _ViewAux:
+    """What the backward pass needs from the primal pass of one view."""
+    __slots__ = ('rays', 'W', 'H', 'spp', 'jit', 'rfilter', 'state', 'accum', 'record')
 
 
 class _RenderOp(torch.autograd.Function):
     """mi.render as a differentiable op: forward = primal render, backward = RBIntegrator.render_backward
-    (re-render the primal with the gradient seed, then the adjoint pass)."""
+    (SURVEY.md section 3.2).  `names` lists the parameter tensors passed in `tensors`, in the same order."""
 
     @staticmethod
-    def forward(ctx, scene, sensor, integrator, seed, seed_grad, spp, spp_grad, jitter, srgb, *tensors):
+    def forward(ctx, scene, sensor, integrator, seed, seed_grad, spp, spp_grad, jitter, srgb, rows, names, *tensors):
         # When the gradient pass would draw exactly the primal's samples (pixel centres, or the same seed and spp), the
-        # primal records its hit lists and the backward pass replays them instead of rendering the primal a second
-        # time (a third of the step in examples/refine_3dg_dataset.py).  Records above 2 GiB per view are not kept.
+        # primal records its hit lists (compressed rows, 4 B per hit) and the backward pass replays them instead of
+        # walking the BVH a second time.  Russian roulette runs in the primal only (reference quirk), so its lists are
+        # not what the adjoint visits: no replay then.
         spp_g = spp_grad or spp
         same_samples = spp_g == spp and (not jitter or seed_grad == seed)
-        views, _ = _views(sensor)
-        cap = integrator._cap()
-        fits = all(v.width * v.height * spp * cap * 4 <= (2 << 30) for v in views)
-        keep = same_samples and fits and REUSE_PRIMAL_RECORDS
-        img, aux = _render_primal(scene, sensor, integrator, seed, spp, jitter, record=keep, srgb=srgb)
-        ctx.args = (scene, sensor, integrator, seed_grad, spp_g, jitter, srgb)
-        ctx.aux = aux if keep else None
-        ctx.n_tensors = len(tensors)
+        keep = same_samples and REUSE_PRIMAL_RECORDS and not getattr(integrator, 'use_rr', False)
+        img, aux = _render_primal(scene, sensor, integrator, seed, spp, jitter, record=keep, srgb=srgb, rows=rows)
+        ctx.args = (scene, sensor, integrator, seed_grad, spp_g, jitter, srgb, rows)
+        ctx.aux = aux if same_samples else None
+        ctx.names = names
         return img
 
     @staticmethod
     def backward(ctx, grad_img):
-        scene, sensor, integrator, seed_grad, spp_grad, jitter, srgb = ctx.args
+        scene, sensor, integrator, seed_grad, spp_grad, jitter, srgb, rows = ctx.args
         shape = scene.ellipsoids()
         shape.zero_grad()
-        _render_adjoint(scene, sensor, integrator, seed_grad, spp_grad, jitter, grad_img.contiguous(), srgb, aux=ctx.aux)
+        _render_adjoint(scene, sensor, integrator, seed_grad, spp_grad, jitter, grad_img.contiguous(), srgb, aux=ctx.aux,
+                        rows=rows)
         ctx.aux = None
         out = []
-        for name in _differentiable_names(shape, integrator):
+        for name in ctx.names:                      # gradients matched to the inputs BY NAME
             g = shape.grad.get(name)
             out.append(None if g is None else g.clone())
-        return (None,) * 9 + tuple(out[:ctx.n_tensors])
+        return (None,) * 11 + tuple(out)
 
 
 def _differentiable_names(shape, integrator):
@@ -386,80 +372,126 @@ class _srgb_override:
             self.integrator.srgb_primitives = self.saved
 
 
-def _render_primal(scene, sensor, integrator, seed, spp, jitter, record, srgb=None):
+def _render_primal(scene, sensor, integrator, seed, spp, jitter, record, srgb=None, rows=None):
     with _srgb_override(integrator, srgb):
-        return _render_primal_impl(scene, sensor, integrator, seed, spp, jitter, record)
+        return _render_primal_impl(scene, sensor, integrator, seed, spp, jitter, record, rows)
 
 
-def _render_primal_impl(scene, sensor, integrator, seed, spp, jitter, record):
+def _render_primal_impl(scene, sensor, integrator, seed, spp, jitter, record, rows):
+    """Per view: rays are generated INSIDE the trace kernel from the sensor (no ray buffers), the film kernels
+    reconstruct the image (box / tent / gaussian at their true radii) straight into the view's column block."""
+    from .accel import RaySource
     shape = scene.ellipsoids()
+    shape.bind(attr_name=integrator.attribute_name, with_sh=integrator.integrator_id == _cabi.INTEGRATOR_RF)
     acc = shape.accel()
     views, rfilter = _views(sensor)
-    images, aux = [], []
+    rf = _rfilter_id(rfilter)
+    params = integrator._vp_params(scene, None)
+    if rows is not None and len(views) != 1:
+        raise Exception("render(rows=...) renders a band of ONE sensor")
+    image, aux, x0, budget = None, [], 0, RECORD_BUDGET_BYTES
+    Wt = sum(v.width for v in views)
     for vi, s in enumerate(views):
         W, H = s.width, s.height
+        band = None
+        if rows is not None:
+            y0, y1 = int(rows[0]), int(rows[1])
+            if not (0 <= y0 < y1 <= H):
+                raise Exception(f"render(rows={rows}): band outside the film (height {H})")
+            if jitter and rfilter != 'box':
+                raise Exception("render(rows=...): a filter wider than a pixel would be cut at the band seams; "
+                                "use the box filter or jitter=False")
+            band, H = (y0, y1 - y0), y1 - y0
         jit = _sample_positions(W, H, spp, seed * 7919 + vi, jitter, shape.device)
-        o, d, maxt = acc.raygen_perspective(s.vp_camera(), spp, jit)
-        image_hint = (W * spp, H) if (W * spp) % 8 == 0 and H % 4 == 0 else None
-        integrator.record_hits = record
-        L, _, _, state = integrator.sample(ADMode.Primal, scene, None, Ray3f(o, d, maxt), image=image_hint)
-        idx, w = _film_weights(W, H, spp, jit, rfilter, shape.device)
-        if idx.shape[1] == 1 and spp == 1:
-            img = L.reshape(H, W, 3)
-            wsum = None
+        rays = RaySource(camera=s.vp_camera(), spp=spp, jitter=jit, rows=band)
+        want = bool(record)
+        if want:   # budget over the views of this call
+            need = int(rays.n_rays * (acc.hits_per_ray_estimate * 1.3 + 4.0) * 4) + rays.n_rays * 8
+            want = need <= budget
+            budget -= need if want else 0
+        res = acc.render_forward(params, rays, record=want, id_cap=integrator._cap(), want_beta=False, want_nhits=False)
+        integrator.last = res
+        direct = spp == 1 and (jit is None or rfilter == 'box')   # every sample is exactly its own pixel
+        accum = None
+        if direct:
+            view_img = res.rgb.reshape(H, W, 3)
+            if len(views) == 1:
+                image = view_img
+            else:
+                if image is None:
+                    image = torch.empty((H, Wt, 3), dtype=torch.float32, device=shape.device)
+                image[:, x0:x0 + W] = view_img
         else:
-            acc_img = torch.zeros((W * H, 3), device=shape.device)
-            wsum = torch.zeros((W * H,), device=shape.device)
-            for k in range(idx.shape[1]):
-                acc_img.index_add_(0, idx[:, k], L * w[:, k:k + 1])
-                wsum.index_add_(0, idx[:, k], w[:, k])
-            img = (acc_img / wsum.clamp_min(1e-12)[:, None]).reshape(H, W, 3)
-        images.append(img)
-        aux.append((o, d, maxt, state, idx, w, wsum, image_hint, integrator.last))
-    return (images[0] if len(images) == 1 else torch.cat(images, dim=1)), aux
+            if image is None:
+                image = torch.empty((H, Wt, 3), dtype=torch.float32, device=shape.device)
+            accum = torch.zeros(W * H * 4, dtype=torch.float32, device=shape.device)
+            acc.film_splat(W, H, spp, rf, jit, res.rgb, accum)
+            acc.film_develop(W, H, accum, image[:, x0:x0 + W])
+        a = _ViewAux()
+        a.rays, a.W, a.H, a.spp, a.jit, a.rfilter, a.state, a.accum, a.record = rays, W, H, spp, jit, rf, res.rgb, accum, res.record
+        aux.append(a)
+        x0 += W
+    return image, aux
 
 
-def _render_adjoint(scene, sensor, integrator, seed, spp, jitter, grad_img, srgb=None, aux=None):
+def _render_adjoint(scene, sensor, integrator, seed, spp, jitter, grad_img, srgb=None, aux=None, rows=None):
     """RBIntegrator.render_backward: primal with the gradient seed, then sample(Backward) with state_in = the
     primal's state_out (volprim_rf.py:192) -- which, with srgb_primitives, is the LINEAR radiance fed into an
     sRGB-space recursion (reference quirk Q3, reproduced when srgb is left at the plugin's own value)."""
-    views, _ = _views(sensor)
     if aux is None:
-        _, aux = _render_primal(scene, sensor, integrator, seed, spp, jitter, record=True, srgb=srgb)
+        _, aux = _render_primal(scene, sensor, integrator, seed, spp, jitter, record=REUSE_PRIMAL_RECORDS and not
+                                getattr(integrator, 'use_rr', False), srgb=srgb, rows=rows)
+    shape = scene.ellipsoids()
+    acc = shape.accel()
     x0 = 0
     with _srgb_override(integrator, srgb):
-        for s, (o, d, maxt, state, idx, w, wsum, image_hint, last) in zip(views, aux):
-            W, H = s.width, s.height
-            g = grad_img[:, x0:x0 + W, :].reshape(W * H, 3)
-            x0 += W
-            if wsum is None:
-                dL = g
+        params = integrator._vp_params(scene, None)
+        out = shape.grad_buffers(integrator.attribute_name)
+        for a in aux:
+            g = grad_img[:, x0:x0 + a.W, :]
+            x0 += a.W
+            if a.accum is None:
+                dL = g.reshape(-1, 3) if g.is_contiguous() else g.contiguous().reshape(-1, 3)
             else:
-                dL = torch.zeros((idx.shape[0], 3), device=g.device)
-                for k in range(idx.shape[1]):
-                    dL += g[idx[:, k]] * (w[:, k] / wsum.clamp_min(1e-12)[idx[:, k]])[:, None]
-            # the recorded lists can be replayed if every ray's list fits the record; with max_depth <= cap that holds
-            # by construction and needs no device->host check (which would stall the launch queue once per view)
-            if last.hit_ids is None:
-                full = False
-            elif int(integrator.max_depth) <= last.hit_ids.shape[0]:
-                full = True
+                dL = acc.film_adjoint(a.W, a.H, a.spp, a.rfilter, a.jit, a.accum, g)
+            rec = a.record
+            if rec is not None:
+                acc.note_record(rec)
+            if rec is not None and rec.usable():
+                acc.render_adjoint(params, a.rays, dL, a.state, rec, out=out)
             else:
-                full = bool((last.nhits <= last.hit_ids.shape[0]).all())
-            integrator.sample(ADMode.Backward, scene, None, Ray3f(o, d, maxt), dL.contiguous(), state, True,
-                              image=image_hint, hit_ids=last.hit_ids if full else None,
-                              hit_counts=last.nhits if full else None)
+                # no (usable) record: re-trace like the primal, on explicit rays of the same sensor samples
+                o, d, maxt = _explicit_rays(acc, a)
+                p2 = integrator._vp_params(scene, (a.W * a.spp, a.H) if (a.W * a.spp) % 8 == 0 and a.H % 4 == 0 else None)
+                acc.trace_adjoint(p2, o, d, maxt, dL, a.state, out=out)
+
+
+def _explicit_rays(acc, a):
+    """Rays of a view (band / jittered) as explicit tensors, for the re-trace fallback of the backward pass."""
+    cam = a.rays.camera
+    if a.rays.rows:
+        y0, n = a.rays.rows
+        full_jit = None
+        if a.jit is not None:
+            full_jit = torch.full((cam.width * cam.height * a.spp, 2), 0.5, dtype=torch.float32, device=acc.device)
+            full_jit[y0 * cam.width * a.spp:(y0 + n) * cam.width * a.spp] = a.jit
+        o, d, maxt = acc.raygen_perspective(cam, a.spp, full_jit)
+        sl = slice(y0 * cam.width * a.spp, (y0 + n) * cam.width * a.spp)
+        return o[sl].contiguous(), d[sl].contiguous(), maxt[sl].contiguous()
+    return acc.raygen_perspective(cam, a.spp, a.jit)
 
 
 def render(scene: Scene, params=None, sensor=0, integrator=None, seed=0, seed_grad=0, spp=0, spp_grad=0,
-           jitter=True, adjoint_mode='reference_exact'):
+           jitter=True, adjoint_mode='reference_exact', rows=None):
     """mi.render(scene, params, sensor, integrator, seed, seed_grad, spp, spp_grad): returns an [H, W, 3]
     CUDA tensor.  When `params` holds tensors with requires_grad, the result carries a grad_fn whose backward
     is the PRB adjoint (`loss.backward()` plays the role of `dr.backward(loss)`).
 
     Extensions: `jitter=False` samples pixel centres (deterministic; the reference always jitters with
     Mitsuba's PCG32 stream, which is third-party); `adjoint_mode='corrected'` differentiates through
-    srgb_to_linear instead of reproducing the reference's colour-space inconsistency (quirk Q3)."""
+    srgb_to_linear instead of reproducing the reference's colour-space inconsistency (quirk Q3);
+    `rows=(y0, y1)` renders only that band of film rows (image-tile sharding over several GPUs,
+    volprim_balance_b200.parallel.render_tiles)."""
     integrator = integrator or scene.integrator
     if not isinstance(integrator, VolprimIntegratorBase):
         raise Exception("render: the scene has no volprim integrator")
@@ -467,23 +499,25 @@ def render(scene: Scene, params=None, sensor=0, integrator=None, seed=0, seed_gr
         sensor = scene.sensors()[sensor]
     spp = int(spp) if spp else 1
     shape = scene.ellipsoids()
-    tensors = []
+    tensors, names = [], []
     if params is not None:
         for name in _differentiable_names(shape, integrator):
             t = params.get(f'{shape.id}.{name}')
             if t is not None:
                 tensors.append(t)
+                names.append(name)
     need_grad = any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors) and torch.is_grad_enabled()
     if not need_grad:
-        return _render_primal(scene, sensor, integrator, seed, spp, jitter, record=False)[0]
+        return _render_primal(scene, sensor, integrator, seed, spp, jitter, record=False, rows=rows)[0]
     if adjoint_mode not in ('reference_exact', 'corrected'):
         raise Exception("adjoint_mode must be 'reference_exact' or 'corrected'")
+    names = tuple(names)
     if adjoint_mode == 'corrected' and getattr(integrator, 'srgb_primitives', False):
         # render in sRGB space and convert with autograd-visible torch ops: the derivative of srgb_to_linear is
         # applied and state_in is the sRGB-space radiance, i.e. the true gradient of the rendered image.
-        img_s = _RenderOp.apply(scene, sensor, integrator, seed, seed_grad, spp, spp_grad, jitter, False, *tensors)
+        img_s = _RenderOp.apply(scene, sensor, integrator, seed, seed_grad, spp, spp_grad, jitter, False, rows, names, *tensors)
         return torch.where(img_s <= 0.04045, img_s / 12.92, ((img_s.clamp_min(0.04045) + 0.055) / 1.055) ** 2.4)
-    return _RenderOp.apply(scene, sensor, integrator, seed, seed_grad, spp, spp_grad, jitter, None, *tensors)
+    return _RenderOp.apply(scene, sensor, integrator, seed, seed_grad, spp, spp_grad, jitter, None, rows, names, *tensors)
 
 
 def render_to_host(scene: Scene, sensors=None, out=None, integrator=None, seed=0, spp=0, jitter=True, on_image=None):

@@ -1,0 +1,156 @@
+"""One optimisation step of the reference's multi-view refinement loop, scheduled for one process per GPU.
+
+Reference: examples/refine_3dg_dataset.py:170-189 --
+    image = mi.render(scene, params, sensor=batch_sensor, spp, seed=it); loss = l1(ref_image, image)
+    dr.backward(loss); opt.step(); update_params(opt)        (update_params -> Ellipsoid.ravel + params.update())
+Here the views of the batch sensor are sharded over the ranks (primitives and LBVH replicated).  Per view: primal pass
+recording compressed hit lists -> L1 gradient of the view -> gather adjoint into ONE flat gradient buffer.  The only
+exchange of the step is the SUM of that buffer; it is cut into primitive ranges, and the all-reduce of range c runs on
+NCCL's stream while the primitive-major accumulation of range c + 1 (last view of the rank) is still running.  Then
+every rank applies the identical BoundedAdam step and refits / rebuilds its own LBVH.
+
+`loss.backward()` through `volprim_balance_b200.render` gives the same gradients (tested); this class exists because
+autograd cannot split the backward pass of the last view into ranges.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi, parallel
+from .accel import RaySource
+from .integrators.common import Ellipsoid
+
+
+class RefineStep:
+    def __init__(self, scene, sensors, targets, opt, n_chunks: int = 4, group=None, rebuild: str = 'rebuild'):
+        """sensors: all views of the batch (PerspectiveSensor objects, identical film sizes); targets: {view index:
+        [H, W, 3] CUDA tensor} for at least the views of this rank; opt: BoundedAdam holding 'centers', 'scales',
+        'quats', 'opacities', 'sh_coeffs' (the keys of refine_3dg_dataset.py:131-153)."""
+        self.scene, self.integrator, self.shape = scene, scene.integrator, scene.ellipsoids()
+        if self.integrator.integrator_id != _cabi.INTEGRATOR_RF:
+            raise Exception("RefineStep drives the volprim_rf integrator")
+        self.sensors, self.targets, self.opt, self.group = list(sensors), targets, opt, group
+        self.rank, self.world = parallel.world()
+        self.views = parallel.shard_views(len(self.sensors), self.rank, self.world)
+        self.n_chunks = n_chunks
+        self.shape.rebuild_policy = rebuild
+        n = self.shape.count
+        shf = self.shape.attributes['sh_coeffs'].numel() // n if n else 0
+        self.bucket = parallel.GradientBucket(n, shf, self.shape.device)
+        self.ranges = parallel.chunk_ranges(n, n_chunks)
+        self.record = None
+        self.timing = {}
+        s0 = self.sensors[0]
+        self.n_pix = len(self.sensors) * s0.width * s0.height * 3
+        self._pinned_totals = torch.zeros((max(len(self.sensors), 1), 2), dtype=torch.int64).pin_memory()
+        self.update_params()
+
+    # refine_3dg_dataset.py:155-159
+    def update_params(self):
+        o = self.opt
+        self.shape.data = Ellipsoid.ravel(o['centers'].detach(), o['scales'].detach(), o['quats'].detach()).contiguous()
+        self.shape.attributes['opacities'] = o['opacities'].detach().reshape(-1).contiguous()
+        self.shape.attributes['sh_coeffs'] = o['sh_coeffs'].detach().reshape(-1).contiguous()
+        self.shape.parameters_changed()
+        self.shape.bind('opacities', with_sh=True)
+
+    def _ensure_record(self, acc, n_rays, id_cap):
+        cap = int(n_rays * min(float(id_cap), acc.hits_per_ray_estimate * 1.3 + 4.0)) + 4096
+        if self.record is None or self.record.capacity < cap or self.record.n_rays != n_rays or self.record.id_cap != id_cap:
+            self.record = acc.new_record(n_rays, id_cap, cap)
+        return self.record
+
+    def step(self, want_images: bool = False):
+        """One optimisation step.  Returns (loss, sum of squared errors / n_pix[, images]) as 0-d CUDA tensors (global
+        over all ranks)."""
+        for _ in range(3):
+            out = self._step_once(want_images)
+            if out is not None:
+                return out
+        raise _cabi.VolprimCudaError("RefineStep: hit records kept overflowing their capacity")
+
+    def accumulate_gradients(self, want_images: bool = False):
+        """Primal + adjoint of this rank's views into the flat gradient buffer; with several ranks the all-reduce of
+        every primitive range is launched (asynchronously, on NCCL's stream) as soon as the last view has accumulated
+        that range.  Returns (bucket, NCCL work handles, (loss, squared error[, images], flags)) -- local, unreduced
+        statistics; the caller waits on the handles."""
+        acc, integ, shape = self.shape.accel(), self.integrator, self.shape
+        params = integ._vp_params(self.scene, None)
+        id_cap = integ._cap()
+        self.bucket.zero_()
+        outs = self.bucket.tensors()
+        loss = torch.zeros((), device=shape.device)
+        sq = torch.zeros((), device=shape.device)
+        flags = torch.zeros(2, device=shape.device)      # records over capacity / rays cut at the per-ray cap
+        works, images = [], {}
+        for k, vi in enumerate(self.views):
+            s = self.sensors[vi]
+            rays = RaySource(camera=s.vp_camera(), spp=1)
+            rec = self._ensure_record(acc, rays.n_rays, id_cap)
+            res = acc.render_forward(params, rays, record=rec, id_cap=id_cap, want_beta=False, want_nhits=False)
+            self._pinned_totals[k % self._pinned_totals.shape[0]].copy_(rec.total, non_blocking=True)
+            flags += torch.stack([(rec.total[0] > rec.capacity).float(), (rec.total[1] > 0).float()])
+            img = res.rgb.reshape(s.height, s.width, 3)
+            diff = img - self.targets[vi]
+            loss += diff.abs().sum() / self.n_pix
+            sq += (diff * diff).sum() / self.n_pix
+            dL = torch.sign(diff).reshape(-1, 3) * (1.0 / self.n_pix)      # d l1(ref, image) / d image
+            if want_images:
+                images[vi] = img
+            acc.adjoint_begin(params, rays, dL, res.rgb, rec, outs)
+            if k + 1 < len(self.views) or self.world == 1:
+                acc.adjoint_finish(params, rays, rec, 0, shape.count, outs)
+            else:
+                # last view of the rank: range by range, each range's all-reduce overlapping the next range's accumulation
+                for p0, p1 in self.ranges:
+                    acc.adjoint_finish(params, rays, rec, p0, p1, outs)
+                    works += self.bucket.all_reduce_chunk(p0, p1, self.group)
+        if not self.views and self.world > 1:
+            for p0, p1 in self.ranges:
+                works += self.bucket.all_reduce_chunk(p0, p1, self.group)
+        return self.bucket, works, ((loss, sq, images, flags) if want_images else (loss, sq, flags))
+
+    def _step_once(self, want_images):
+        acc = self.shape.accel()
+        ev = {k: torch.cuda.Event(enable_timing=True) for k in ('start', 'compute_done', 'comm_done', 'end')}
+        ev['start'].record()
+        _, works, stats_local = self.accumulate_gradients(want_images)
+        loss, sq, flags = stats_local[0], stats_local[1], stats_local[-1]
+        images = stats_local[2] if want_images else None
+        ev['compute_done'].record()
+        for w in works:
+            w.wait()
+        ev['comm_done'].record()
+        # Every record must have fitted its capacity (the kernels skip an unusable record), and ALL ranks must take
+        # the same decision: the overflow flags travel with the loss statistics.
+        stats = torch.stack([loss, sq, flags[0], flags[1]])
+        if self.world > 1:
+            dist.all_reduce(stats, group=self.group)
+        loss, sq = stats[0], stats[1]
+        torch.cuda.current_stream().synchronize()
+        if len(self.views):
+            entries = int(self._pinned_totals[:len(self.views), 0].max())
+            acc.hits_per_ray_estimate = max(4.0, entries / max(self.record.n_rays, 1))
+        _, _, overflowed, cut = stats.tolist()
+        if cut:
+            raise _cabi.VolprimCudaError("RefineStep: a ray recorded more hits than the integrator's record cap")
+        if overflowed:
+            return None                # redo the step with records sized from the new estimate
+        # identical optimiser step on every rank (refine_3dg_dataset.py:178-189)
+        g = self.bucket.data.view(-1, 10)
+        o = self.opt
+        o['centers'].grad = g[:, 0:3].contiguous()
+        o['scales'].grad = g[:, 3:6].contiguous()
+        o['quats'].grad = g[:, 6:10].contiguous()
+        o['opacities'].grad = self.bucket.attr.reshape(o['opacities'].shape).clone()
+        o['sh_coeffs'].grad = self.bucket.sh.reshape(o['sh_coeffs'].shape).clone()
+        o.step()
+        self.update_params()
+        ev['end'].record()
+        torch.cuda.current_stream().synchronize()
+        self.timing = {'step_ms': ev['start'].elapsed_time(ev['end']),
+                       'exposed_allreduce_ms': ev['compute_done'].elapsed_time(ev['comm_done']),
+                       'optimizer_and_rebuild_ms': ev['comm_done'].elapsed_time(ev['end']),
+                       'allreduce_bytes': self.bucket.flat.numel() * 4 if self.world > 1 else 0}
+        return (loss, sq, images) if want_images else (loss, sq)
