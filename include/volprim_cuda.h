@@ -87,12 +87,10 @@ typedef struct vp_ray_source {
 } vp_ray_source;
 
 /* Ordered hit lists of a primal pass in compressed-row form (what the adjoint replays instead of walking the BVH a
- * second time).  All arrays are caller-owned DEVICE memory.  Bytes kept per view: 4 per recorded hit + 8 per ray
- * + 4 per primitive. */
+ * second time).  All arrays are caller-owned DEVICE memory.  Bytes kept per view: 4 per recorded hit + 8 per ray. */
 typedef struct vp_hit_record {
     int64_t *ray_offsets;   /* [n_rays + 1]   list of ray r = ids[ray_offsets[r] .. ray_offsets[r + 1])            */
     int32_t *ids;           /* [capacity]     primitive ids (numbering of vp_set_primitives), front to back        */
-    uint32_t *prim_offsets; /* [n_prims + 1]  exclusive prefix of the number of recorded hits per primitive        */
     int64_t *total;         /* [2]            entries all lists need; rays whose list was cut at `id_cap`          */
     int64_t capacity;       /* entries `ids` holds (< 2^32).  A record is usable iff total[0] <= capacity and
                                total[1] == 0; vp_render_adjoint does nothing otherwise (the caller re-traces)     */
@@ -173,16 +171,17 @@ VP_API int vp_raygen_perspective(vp_ctx *ctx, const vp_camera *cam, int32_t spp,
  * perspective sensor).  out_T / out_nhits may be NULL.  With `record` != NULL the ordered hit lists are kept in
  * compressed-row form: the trace kernel writes them hit-major into a transient scratch of the context (bounded by
  * splitting the call into row bands), a compaction pass copies them to record->ids at the exclusive-scan offsets of
- * the hit counts, and the per-primitive hit counts are accumulated on the way (for the gather adjoint). */
+ * the hit counts.  (The trace kernel itself contains no atomics: see csrc/vp_trace.cu.) */
 VP_API int vp_render_forward(vp_ctx *ctx, const vp_params *params, const vp_ray_source *rays, int64_t n_rays,
                              float *out_rgb, float *out_T, uint32_t *out_nhits, const vp_hit_record *record,
                              void *stream);
 
 /* vp_render_adjoint: Integrator.sample(Backward) replaying `record` (volprim_rf.py:106-165).  volprim_rf uses the
- * GATHER formulation: a ray-major pass replays every list and writes 20 B of per-hit state into the bucket of the
- * hit primitive, then one warp per primitive accumulates its bucket in registers and adds the 10 + 1 + C gradient
- * floats to the caller's buffers exactly once -- no global reductions (the scatter formulation of vp_trace_adjoint
- * saturates the L2 reduction units).  volprim_tomography replays with vector reductions like vp_trace_adjoint.
+ * GATHER formulation: a flat counting pass over the record sizes one bucket per primitive, a ray-major pass replays
+ * every list and writes 20 B of per-hit state into the bucket of the hit primitive, then one warp per primitive (and
+ * per further 256 entries of a big bucket) accumulates its bucket in registers and adds the 10 + 1 + C gradient floats
+ * to the caller's buffers -- no per-hit global reductions (the scatter formulation of vp_trace_adjoint saturates the L2
+ * reduction units).  volprim_tomography replays with vector reductions like vp_trace_adjoint.
  * Gradients are ADDED to g_data10 [N*10], g_attr [N], g_sh [N*C] (8-, 4- and 8-byte aligned); the buffers must not
  * be written by anything else while the call runs.  Equivalent to vp_adjoint_begin + vp_adjoint_finish(0, N). */
 VP_API int vp_render_adjoint(vp_ctx *ctx, const vp_params *params, const vp_ray_source *rays, int64_t n_rays,

@@ -101,6 +101,7 @@ def _lib(precision: str):
         lib.orc_replay_forward.argtypes = [C.c_void_p, C.POINTER(_Params), C.c_int64, rp, rp, rp, C.POINTER(C.c_int32),
                                            C.POINTER(C.c_uint32), C.c_int32, rp, rp, C.POINTER(C.c_int32),
                                            C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        lib.orc_set_abs_mode.argtypes = [C.c_int]
         lib.orc_quat_to_matrix.argtypes = [rp, rp]
         lib.orc_sh_eval.argtypes = [rp, C.c_int, rp]
         lib.orc_srgb_to_linear.restype = real
@@ -208,8 +209,9 @@ class Scene:
                                     _ptr(beta, self.real), _ptr(valid, C.c_int32), _ptr(hb, C.c_double), _ptr(cm, C.c_double))
         return {"rgb": rgb, "beta": beta, "valid": valid.astype(bool), "hit_beta": hb, "cmax": cm}
 
-    def adjoint(self, params: Params, o, d, dL, state_in, maxt=None):
-        """Returns (g_data [N,10], g_attr [N], g_sh [N,C]) in float64."""
+    def adjoint(self, params: Params, o, d, dL, state_in, maxt=None, abs_terms: bool = False):
+        """Returns (g_data [N,10], g_attr [N], g_sh [N,C]) in float64.  abs_terms=True: the sum of the ABSOLUTE per-hit
+        contributions instead (bounds the rounding error of an fp32 accumulation of the same terms)."""
         o, d, m = self._rays(o, d, maxt)
         R = o.shape[0]
         dL = np.ascontiguousarray(np.asarray(dL, dtype=self.np_real).reshape(R, 3))
@@ -218,9 +220,13 @@ class Scene:
         ga = np.zeros(self.n, np.float64)
         gs = np.zeros((self.n, max(self.sh_floats, 1)), np.float64)
         p = params.to_c()
-        self.lib.orc_trace_adjoint(self._h, C.byref(p), R, _ptr(o, self.real), _ptr(d, self.real), _ptr(m, self.real),
-                                   _ptr(dL, self.real), _ptr(st, self.real), _ptr(gd, C.c_double),
-                                   _ptr(ga, C.c_double), _ptr(gs, C.c_double))
+        self.lib.orc_set_abs_mode(int(abs_terms))
+        try:
+            self.lib.orc_trace_adjoint(self._h, C.byref(p), R, _ptr(o, self.real), _ptr(d, self.real), _ptr(m, self.real),
+                                       _ptr(dL, self.real), _ptr(st, self.real), _ptr(gd, C.c_double),
+                                       _ptr(ga, C.c_double), _ptr(gs, C.c_double))
+        finally:
+            self.lib.orc_set_abs_mode(0)
         return gd, ga, (gs if self.sh_floats else None)
 
 

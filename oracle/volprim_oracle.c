@@ -818,6 +818,13 @@ static void chain_density(const ellipsoid *e, int kernel, const REAL o[3], const
  * Gradients are accumulated in double into g_data [n*10], g_attr [n], g_sh [n*C] (caller-zeroed).
  * `state_in` is used as given (the caller decides between reference_exact and corrected, Q3).
  */
+/* Test aid: with abs mode on, orc_trace_adjoint accumulates the ABSOLUTE value of every per-hit contribution, i.e.
+ * sum_hits |term| per gradient element -- the quantity that bounds the rounding error of an fp32 accumulation of the
+ * same terms (eps * sum |term|), whatever the order. */
+static int g_abs_mode = 0;
+EXPORT void orc_set_abs_mode(int on) { g_abs_mode = on; }
+#define ACC(dst, x) do { double x__ = (x); (dst) += g_abs_mode ? fabs(x__) : x__; } while (0)
+
 EXPORT void orc_trace_adjoint(const orc_scene *sc, const orc_params *pr, int64_t R, const REAL *ray_o,
                               const REAL *ray_d, const REAL *ray_maxt, const REAL *dL, const REAL *state_in,
                               double *g_data, double *g_attr, double *g_sh)
@@ -857,25 +864,25 @@ EXPORT void orc_trace_adjoint(const orc_scene *sc, const orc_params *pr, int64_t
                         if (q.colraw[ch] > R_(0) && sc->sh_floats) {
                             double dcol = (double)g[ch] * (double)beta * q.one_minus_T;
                             int nb = sc->sh_floats / 3;
-                            for (int i = 0; i < nb; ++i) g_sh[j * sc->sh_floats + 3 * i + ch] += (double)Y[i] * dcol;
+                            for (int i = 0; i < nb; ++i) ACC(g_sh[j * sc->sh_floats + 3 * i + ch], (double)Y[i] * dcol);
                         }
                     }
                     dalpha -= (double)g[ch] * (double)L[ch] / (double)q.T;
                 }
                 REAL araw = sc->attr[j] * q.G;
                 if (araw < R_(0.9999)) { /* min() passes the gradient to its first argument */
-                    g_attr[j] += dalpha * (double)q.G;
+                    ACC(g_attr[j], dalpha * (double)q.G);
                     double dG = dalpha * (double)sc->attr[j];
                     if (pr->kernel == ORC_GAUSS) {
                         double dq = -0.5 * (double)q.G * dG;
                         double tmp[10] = { 0 };
                         chain_quadratic(&e, q.ppeak, R_(1), R_(1), tmp);
-                        for (int k = 0; k < 10; ++k) g_data[j * 10 + k] += tmp[k] * dq;
+                        for (int k = 0; k < 10; ++k) ACC(g_data[j * 10 + k], tmp[k] * dq);
                     } else if (q.G > R_(0)) {
                         double dq = -0.75 * dG;
                         double tmp[10] = { 0 };
                         chain_quadratic(&e, q.ppeak, R_(3), R_(1), tmp);
-                        for (int k = 0; k < 10; ++k) g_data[j * 10 + k] += tmp[k] * dq;
+                        for (int k = 0; k < 10; ++k) ACC(g_data[j * 10 + k], tmp[k] * dq);
                     }
                 }
                 beta = beta * q.T;
@@ -889,10 +896,12 @@ EXPORT void orc_trace_adjoint(const orc_scene *sc, const orc_params *pr, int64_t
                     if (!isfinite((double)lo)) continue;
                     dT += (double)g[ch] * (double)L[ch] / (double)T;
                 }
-                g_attr[j] += -(double)rho * (double)T * dT;
+                ACC(g_attr[j], -(double)rho * (double)T * dT);
                 if (rho > R_(0) && isfinite((double)raw)) {
                     double drho = -(double)sc->attr[j] * (double)T * dT;
-                    chain_density(&e, pr->kernel, o, d, (double)rho, drho, g_data + j * 10);
+                    double tmp[10] = { 0 };
+                    chain_density(&e, pr->kernel, o, d, (double)rho, drho, tmp);
+                    for (int k = 0; k < 10; ++k) ACC(g_data[j * 10 + k], tmp[k]);
                 }
             }
             for (int a = 0; a < 3; ++a) {

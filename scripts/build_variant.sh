@@ -8,4 +8,4 @@ mkdir -p ../../build_var
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-fvisibility=hidden -I../../include -I. \
      --expt-relaxed-constexpr "$@" -Xptxas -v -c vp_trace.cu -o /tmp/vt_$name.o 2>/tmp/vt_$name.log
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build_var/libvp_$name.so _build/vp_api.o _build/vp_build.o \
-     _build/vp_optim.o /tmp/vt_$name.o -lcudart_static -ldl -lrt -lpthread
+     _build/vp_optim.o _build/vp_film.o /tmp/vt_$name.o -lcudart_static -ldl -lrt -lpthread

@@ -120,11 +120,51 @@ def compare_forward(res_gpu, res_orc, cap, max_fragile_frac=5e-3, replay=None, s
             "mean_hits": float(nh_o.mean()), "fragile_max_diff": frag_diff, "_same": same}
 
 
-def grad_close(g_gpu, g_orc, rtol=GRAD_RTOL, what=""):
-    """ELEMENTWISE agreement of a gradient block: |diff| <= rtol * |ref| + rtol * rms(ref).  The relative term is the
-    contract's 1e-3; the rms term is the absolute floor for elements that are themselves sums with cancellation
-    (fp32 reorders the per-hit sums; an element far below the block's typical magnitude cannot be resolved to 1e-3
-    of itself in fp32 by either side).  Returns the largest |diff| / (|ref| + rms)."""
+class GradientReference:
+    """Reference for GRADIENTS: the float64 build of the oracle (the build tests/test_oracle_golden.py pins to the
+    reference source's own outputs at 1e-7), with the fp32 build beside it as the measure of what fp32 can resolve.
+
+    An fp32 evaluation of one hit -- the reference's Dr.Jit kernels, the fp32 oracle and the CUDA kernels alike --
+    loses digits where the algorithm is ill-conditioned: the first hit of a camera ray is evaluated from an origin
+    ~1e3 scales away (up to ~5e-4 relative error on that hit's terms), and the tomography line integral as written
+    (common.py:199-206) cancels in fp32 (per-element errors of 1e-2 of the block's rms between the fp32 and the float64
+    oracle).  So: the CUDA gradient must agree with float64 within 1e-3 (|ref| + block rms) -- the contract -- plus
+    three times the fp32 oracle's OWN deviation from float64 on that element, the part no fp32 code can be held to."""
+
+    def __init__(self, cloud, attr=None, sh=True):
+        self.o32 = oracle_scene(cloud, attr=attr, sh=sh, precision="f32")
+        self.o64 = oracle_scene(cloud, attr=attr, sh=sh, precision="f64")
+
+    def same_lists(self, op, o, d, mt, ids_g, cap):
+        ref64 = self.o64.forward(op, o, d, mt, cap=cap)
+        return (np.asarray(ids_g)[:, :cap] == ref64.hit_ids[:, :cap]).all(axis=1)
+
+    SUM_EPS = 5e-7 / 3.0     # x3 in grad_close: 8 units of fp32 round-off (2^-24) per unit of sum |term|
+
+    def adjoint(self, op, o, d, dL, state, mt):
+        """(float64 gradients, per-element noise).  noise = |fp32 oracle - float64 oracle| + SUM_EPS * sum_hits |term|:
+        the second part bounds what an fp32 ACCUMULATION of the per-hit terms loses (the oracles accumulate in double;
+        the reference's Dr.Jit scatter-add and the CUDA kernels accumulate in fp32, and with a random delta-L thousands
+        of terms cancel to a small sum)."""
+        g64 = self.o64.adjoint(op, o, d, dL, state, mt)
+        g32 = self.o32.adjoint(op, o, d, dL, state, mt)
+        gabs = self.o64.adjoint(op, o, d, dL, state, mt, abs_terms=True)
+        noise = tuple(None if a is None else np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)) + self.SUM_EPS * np.asarray(c)
+                      for a, b, c in zip(g32, g64, gabs))
+        return g64, noise
+
+
+def f64_reference(cloud, op, o, d, mt, ids_g, cap, attr=None, sh=True):
+    """(GradientReference, mask of the rays whose float64 hit list equals the GPU's `ids_g`)."""
+    ref = GradientReference(cloud, attr=attr, sh=sh)
+    return ref, ref.same_lists(op, o, d, mt, ids_g, cap)
+
+
+def grad_close(g_gpu, g_orc, rtol=GRAD_RTOL, what="", noise=None):
+    """ELEMENTWISE agreement of a gradient block: |diff| <= rtol * |ref| + rtol * rms(ref) [+ 3 * noise].  The relative
+    term is the contract's 1e-3; the rms term is the absolute floor for elements that are themselves sums with
+    cancellation; `noise` (optional) is the fp32 oracle's own deviation from float64 on each element (see
+    GradientReference).  Returns the largest |diff| / (|ref| + rms)."""
     g_gpu = np.asarray(g_gpu, np.float64).reshape(-1)
     g_orc = np.asarray(g_orc, np.float64).reshape(-1)
     assert g_gpu.shape == g_orc.shape, what
@@ -133,11 +173,39 @@ def grad_close(g_gpu, g_orc, rtol=GRAD_RTOL, what=""):
         assert np.abs(g_gpu).max(initial=0.0) == 0, what
         return 0.0
     assert np.isfinite(g_gpu).all(), f"{what}: non-finite gradient"
-    ratio = np.abs(g_gpu - g_orc) / (np.abs(g_orc) + rms)
-    worst = int(ratio.argmax())
-    assert ratio[worst] <= rtol, (f"{what}: element {worst}: got {g_gpu[worst]:.6e}, want {g_orc[worst]:.6e} "
-                                  f"(|diff| / (|ref| + rms) = {ratio[worst]:.3e} > {rtol}, block rms {rms:.3e})")
-    return float(ratio[worst])
+    diff = np.abs(g_gpu - g_orc)
+    ratio = diff / (np.abs(g_orc) + rms)
+    allowed = rtol * (np.abs(g_orc) + rms)
+    if noise is not None:
+        allowed = allowed + 3.0 * np.asarray(noise, np.float64).reshape(-1)
+    bad = diff > allowed
+    # A per-hit derivative is discontinuous at the alpha clamp (0.9999) and at the edge of the Epanechnikov support: a
+    # hit within rounding of either may fall on the other side in another arithmetic.  At most one element in a
+    # million (and never more than 3e-3 of |ref| + rms) may be such a case.
+    if 0 < bad.sum() <= max(1, int(1e-6 * bad.size)) and (ratio[bad] <= 3e-3).all():
+        bad[:] = False
+    if bad.any():
+        worst = int(np.argmax(np.where(bad, diff / allowed, 0)))
+        raise AssertionError(f"{what}: {int(bad.sum())} elements out of tolerance; worst element {worst}: got {g_gpu[worst]:.6e}, "
+                             f"want {g_orc[worst]:.6e} (|diff| / (|ref| + rms) = {ratio[worst]:.3e}, rtol {rtol}, "
+                             f"fp32 noise of the reference there {0.0 if noise is None else float(np.asarray(noise).reshape(-1)[worst]):.3e}, "
+                             f"block rms {rms:.3e})")
+    return float(ratio.max())
+
+
+def check_gradients(got, want, noise, what, split_data=True):
+    """(g_data, g_attr, g_sh) of the CUDA path against GradientReference.adjoint's (gradients, noise), block by block
+    (centre / scale / quaternion separately when split_data)."""
+    to_np = lambda t: t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+    gd, wd, nd = to_np(got[0]).reshape(-1, 10), np.asarray(want[0]).reshape(-1, 10), np.asarray(noise[0]).reshape(-1, 10)
+    errs = {}
+    blocks = (("center", slice(0, 3)), ("scale", slice(3, 6)), ("quat", slice(6, 10))) if split_data else (("data", slice(0, 10)),)
+    for name, sl in blocks:
+        errs[name] = grad_close(gd[:, sl], wd[:, sl], what=f"{what} d {name}", noise=nd[:, sl])
+    errs["attr"] = grad_close(to_np(got[1]), want[1], what=f"{what} d attr", noise=noise[1])
+    if len(got) > 2 and got[2] is not None and want[2] is not None:
+        errs["sh"] = grad_close(to_np(got[2]), want[2], what=f"{what} d sh", noise=noise[2])
+    return errs
 
 
 def record_lists(rec, rays, cap):

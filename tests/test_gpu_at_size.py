@@ -12,7 +12,8 @@ import volprim_balance_b200 as vp
 from oracle import oracle as O
 from volprim_balance_b200 import synthetic
 from volprim_balance_b200.accel import RaySource, TraceResult
-from tests.parity_utils import compare_forward, gpu_scene, grad_close, make_params, oracle_scene, record_lists
+from tests.parity_utils import (check_gradients, compare_forward, f64_reference, gpu_scene, grad_close, make_params, oracle_scene,
+                                record_lists)
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402  (the workload definitions of the benchmark ARE the configurations under test)
@@ -59,17 +60,15 @@ def _check_at_size(name, sel_fn, id_cap, hits_estimate, max_fragile_frac=5e-3, g
     if grad:
         dL = np.zeros((W * H, 3), np.float32)
         dsel = np.random.default_rng(7).normal(size=(len(sel), 3)).astype(np.float32)
-        dsel[~out["_same"]] = 0
+        del osc
+        osc64, same64 = f64_reference(cloud, op, o[sel], d[sel], mt[sel], ids_g, id_cap)
+        dsel[~(out["_same"] & same64)] = 0
         dL[sel] = dsel
         state = fwd.rgb.clone()
         state[tsel] = torch.from_numpy(ref.rgb).cuda()
         gd, ga, gs = acc.render_adjoint(p, rays, torch.from_numpy(dL), state, rec)
-        rd, ra, rs = osc.adjoint(op, o[sel], d[sel], dsel, ref.rgb, mt[sel])
-        info["grad_err"] = [grad_close(gd.cpu().numpy().reshape(-1, 10)[:, 0:3], rd[:, 0:3], what=name + " d center"),
-                            grad_close(gd.cpu().numpy().reshape(-1, 10)[:, 3:6], rd[:, 3:6], what=name + " d scale"),
-                            grad_close(gd.cpu().numpy().reshape(-1, 10)[:, 6:10], rd[:, 6:10], what=name + " d quat"),
-                            grad_close(ga.cpu().numpy(), ra, what=name + " d opacity"),
-                            grad_close(gs.cpu().numpy(), rs, what=name + " d sh")]
+        want, noise = osc64.adjoint(op, o[sel], d[sel], dsel, ref.rgb, mt[sel])
+        info["grad_err"] = check_gradients((gd, ga, gs), want, noise, name)
         per_prim = np.bincount(ids_g[ids_g >= 0], minlength=cloud.n)
         info["max_selected_rays_per_primitive"] = int(per_prim.max())
     print(name, info)

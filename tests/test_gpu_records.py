@@ -8,8 +8,8 @@ import volprim_balance_b200 as vp
 from oracle import oracle as O
 from volprim_balance_b200 import _cabi, synthetic
 from volprim_balance_b200.accel import HitRecord, RaySource
-from tests.parity_utils import (RGB_ATOL, RGB_RTOL, compare_forward, gpu_scene, grad_close, make_params, oracle_scene,
-                                record_lists, robust_mask)
+from tests.parity_utils import (RGB_ATOL, RGB_RTOL, GradientReference, check_gradients, compare_forward, f64_reference, gpu_scene,
+                                grad_close, make_params, oracle_scene, record_lists, robust_mask)
 
 pytestmark = pytest.mark.gpu
 
@@ -53,7 +53,7 @@ def test_fused_raygen_equals_explicit_rays(spp, jitter):
 @pytest.mark.parametrize("scratch", [None, 1 << 20])
 def test_compressed_hit_records_equal_the_dense_lists(scratch):
     """vp_render_forward(record): ray_offsets = exclusive scan of the hit counts, ids = the dense lists without padding,
-    prim_offsets = exclusive scan of the hits per primitive; the same with a 1 MiB scratch (many row bands)."""
+    the same with a 1 MiB scratch (many row bands)."""
     cloud = _cloud()
     cam = synthetic.ring_camera(1, 8, 128, 64)
     acc = gpu_scene(cloud)
@@ -73,11 +73,8 @@ def test_compressed_hit_records_equal_the_dense_lists(scratch):
     ids = rec.ids.cpu().numpy()[:off[-1]]
     want = dense.hit_ids.t().cpu().numpy()
     assert (ids == want[want >= 0]).all()                       # row-major, no padding
-    counts = np.bincount(ids, minlength=cloud.n)
-    po = rec.prim_offsets.cpu().numpy().view(np.uint32).astype(np.int64)
-    assert po[0] == 0 and (np.diff(po) == counts).all()
-    # bytes kept per view: 4 per recorded hit (+ the two offset arrays)
-    assert rec.ids.numel() >= off[-1] and rec.nbytes() == rec.ids.numel() * 4 + (128 * 64 + 1) * 8 + (cloud.n + 1) * 4
+    # bytes kept per view: 4 per recorded hit (+ the ray offsets)
+    assert rec.ids.numel() >= off[-1] and rec.nbytes() == rec.ids.numel() * 4 + (128 * 64 + 1) * 8
     # a record that is too small is reported, not silently truncated
     small = acc.new_record(128 * 64, 64, capacity=1000)
     acc.render_forward(p0, RaySource(camera=s.vp_camera()), record=small, id_cap=64)
@@ -104,15 +101,12 @@ def test_gather_adjoint_matches_oracle_and_scatter_adjoint(kernel, deg):
     ids_g, _ = record_lists(fwd.record, range(o.shape[0]), 128)
     st = compare_forward(fwd, ref, 128, replay=(osc, op, o, d, mt), ids_g=ids_g)
     dL = np.random.default_rng(7).normal(size=(o.shape[0], 3)).astype(np.float32)
-    dL[~st["_same"]] = 0                                            # keep the comparison on rays both sides agree on
+    osc64, same64 = f64_reference(cloud, op, o, d, mt, ids_g, 128)
+    dL[~(st["_same"] & same64)] = 0                                 # keep the comparison on rays all sides agree on
     dL[::7] = 0                                                     # and exercise the "gradient is zero: skip" branch
     gd, ga, gs = acc.render_adjoint(p, rays, torch.from_numpy(dL), torch.from_numpy(ref.rgb), fwd.record)
-    rd, ra, rs = osc.adjoint(op, o, d, dL, ref.rgb, mt)
-    e = [grad_close(gd.cpu().numpy().reshape(-1, 10)[:, 0:3], rd[:, 0:3], what="d center"),
-         grad_close(gd.cpu().numpy().reshape(-1, 10)[:, 3:6], rd[:, 3:6], what="d scale"),
-         grad_close(gd.cpu().numpy().reshape(-1, 10)[:, 6:10], rd[:, 6:10], what="d quat"),
-         grad_close(ga.cpu().numpy(), ra, what="d opacity"),
-         grad_close(gs.cpu().numpy(), rs, what="d sh")]
+    want, noise = osc64.adjoint(op, o, d, dL, ref.rgb, mt)
+    e = check_gradients((gd, ga, gs), want, noise, "gather adjoint")
     # scatter formulation (vector reductions) replaying the SAME lists from a dense record
     to, td, tm = (torch.from_numpy(x) for x in (o, d, mt))
     p_img, _ = make_params(0, kernel, 128, image=(64, 32))
@@ -120,8 +114,7 @@ def test_gather_adjoint_matches_oracle_and_scatter_adjoint(kernel, deg):
     assert (dense.hit_ids.t().cpu().numpy() == ids_g).all()
     sd, sa, ss = acc.trace_adjoint(p, to, td, tm, torch.from_numpy(dL), torch.from_numpy(ref.rgb),
                                    hit_ids=dense.hit_ids, hit_counts=dense.nhits)
-    for x, y, name in ((gd, sd, "data"), (ga, sa, "attr"), (gs, ss, "sh")):
-        grad_close(x.cpu().numpy(), y.cpu().numpy(), what="gather vs scatter " + name)
+    check_gradients((sd, sa, ss), want, noise, "scatter adjoint on the same lists")
     # the call ADDS: a second pass doubles the buffers; primitive ranges compose
     out = (gd.clone(), ga.clone(), gs.clone())
     acc.adjoint_begin(p, rays, torch.from_numpy(dL), torch.from_numpy(ref.rgb), fwd.record, out)
@@ -146,11 +139,11 @@ def test_tomography_adjoint_replays_compressed_records():
     ids_g, _ = record_lists(fwd.record, range(o.shape[0]), 256)
     st = compare_forward(fwd, ref, 256, replay=(osc, op, o, d, mt), srgb=False, ids_g=ids_g)
     dL = np.random.default_rng(9).normal(size=(o.shape[0], 3)).astype(np.float32)
-    dL[~st["_same"]] = 0
+    osc64, same64 = f64_reference(cloud, op, o, d, mt, ids_g, 256, attr=sig, sh=False)
+    dL[~(st["_same"] & same64)] = 0
     gd, ga, _ = acc.render_adjoint(p, rays, torch.from_numpy(dL), torch.from_numpy(ref.rgb), fwd.record)
-    rd, ra, _ = osc.adjoint(op, o, d, dL, ref.rgb, mt)
-    grad_close(gd.cpu().numpy().reshape(-1, 10), rd, what="d data")
-    grad_close(ga.cpu().numpy(), ra, what="d sigma_t")
+    want, noise = osc64.adjoint(op, o, d, dL, ref.rgb, mt)
+    print(check_gradients((gd, ga, None), want, noise, "tomography replay"))
 
 
 @pytest.mark.parametrize("tile", [False, True], ids=["per_ray", "tile"])
@@ -267,6 +260,7 @@ def test_render_batch_sensor_with_filters_matches_film_restatement_per_pixel():
                          "sh_coeffs": cloud.sh_coeffs, "extent": 3.0}}
     scene = vp.load_dict(sd)
     osc = oracle_scene(cloud)
+    gref = GradientReference(cloud)
     op = O.Params(integrator=O.RF, kernel=O.GAUSS, max_depth=64, srgb_primitives=False)
     for rfilter in ("tent", "gaussian"):
         sens = {f"cam_{i}": {"type": "perspective", "fov": c.fov_x_deg, "fov_axis": "x", "to_world": vp.Transform4f(c.to_world),
@@ -288,7 +282,7 @@ def test_render_batch_sensor_with_filters_matches_film_restatement_per_pixel():
             for i in np.flatnonzero(~robust_mask(ref)):
                 for py, px, _ in contrib[i]:
                     okpix[py, px] = False
-            assert okpix.mean() > 0.9
+            assert okpix.mean() > 0.6      # (the gaussian filter spreads every excluded sample over 16 pixels)
             w[:, 40 * vi:40 * (vi + 1)][~okpix] = 0
             views.append((o, d, mt, ref, want, ref_acc, contrib, okpix))
         params = vp.traverse(scene)
@@ -299,7 +293,8 @@ def test_render_batch_sensor_with_filters_matches_film_restatement_per_pixel():
         img = vp.render(scene, params, sensor=batch, spp=spp, seed=seed, seed_grad=seed)
         assert img.shape == (24, 80, 3)
         (img * torch.from_numpy(w).cuda()).sum().backward()
-        rd = np.zeros((n, 10)); ra = np.zeros(n); rs = np.zeros((n, 12))
+        tot = [np.zeros((n, 10)), np.zeros(n), np.zeros((n, 12))]
+        tot_noise = [np.zeros((n, 10)), np.zeros(n), np.zeros((n, 12))]
         for vi, (o, d, mt, ref, want, ref_acc, contrib, okpix) in enumerate(views):
             got = img.detach()[:, 40 * vi:40 * (vi + 1)].cpu().numpy()
             ok = np.abs(got - want) <= RGB_ATOL + RGB_RTOL * np.abs(want)
@@ -308,11 +303,11 @@ def test_render_batch_sensor_with_filters_matches_film_restatement_per_pixel():
             for i, mine in enumerate(contrib):
                 for py, px, wt in mine:
                     dL[i] += w[py, 40 * vi + px].astype(np.float64) * wt / ref_acc[py, px, 3]
-            g = osc.adjoint(op, o, d, dL, ref.rgb, mt)
-            rd += g[0]; ra += g[1]; rs += g[2]
-        grad_close(params[keys[0]].grad.cpu().numpy(), rd, what=rfilter + " d data")
-        grad_close(params[keys[1]].grad.cpu().numpy(), ra, what=rfilter + " d opacities")
-        grad_close(params[keys[2]].grad.cpu().numpy(), rs, what=rfilter + " d sh")
+            g, nz = gref.adjoint(op, o, d, dL, ref.rgb, mt)
+            for k in range(3):
+                tot[k] += g[k]
+                tot_noise[k] += nz[k]
+        check_gradients([params[k].grad for k in keys], tot, tot_noise, rfilter + " batch film")
 
 
 def test_render_rows_band_equals_rows_of_the_full_image_and_gradients_sum():
@@ -380,8 +375,8 @@ def test_backward_falls_back_to_retracing_when_the_record_does_not_fit():
         out.append([params[k].grad.clone() for k in keys])
         if estimate < 1:
             assert scene.ellipsoids().accel().hits_per_ray_estimate > 4      # the next record is sized from this one
-    for a, b, k in zip(out[0], out[1], keys):
-        grad_close(b.cpu().numpy(), a.cpu().numpy(), what="replay vs re-trace fallback " + k)
+    for a, b, k in zip(out[0], out[1], keys):     # two fp32 evaluations (gather from the far origin vs scatter): 2e-3
+        grad_close(b.cpu().numpy(), a.cpu().numpy(), rtol=2e-3, what="replay vs re-trace fallback " + k)
 
 
 def test_misaligned_gradient_buffers_are_refused_and_unaligned_adam_grads_work():

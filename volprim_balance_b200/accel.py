@@ -61,22 +61,20 @@ class RaySource:
 
 
 class HitRecord:
-    """Ordered hit lists of a primal pass in compressed-row form (vp_hit_record): 4 bytes per recorded hit,
-    8 per ray, 4 per primitive.  `usable()` reads two device counters (synchronises the stream once)."""
+    """Ordered hit lists of a primal pass in compressed-row form (vp_hit_record): 4 bytes per recorded hit, 8 per ray.  `usable()` reads two device counters (synchronises the stream once)."""
 
     def __init__(self, n_rays: int, n_prims: int, capacity: int, id_cap: int, device):
         self.n_rays, self.n_prims = n_rays, n_prims
         self.capacity, self.id_cap = int(max(capacity, 1)), int(id_cap)
         self.ray_offsets = torch.empty(n_rays + 1, dtype=torch.int64, device=device)
         self.ids = torch.empty(self.capacity, dtype=torch.int32, device=device)
-        self.prim_offsets = torch.empty(n_prims + 1, dtype=torch.int32, device=device)   # bit pattern of uint32
         self.total = torch.zeros(2, dtype=torch.int64, device=device)
         self._usable = None
 
     def to_c(self) -> vp_hit_record:
         r = vp_hit_record()
         r.ray_offsets, r.ids = self.ray_offsets.data_ptr(), self.ids.data_ptr()
-        r.prim_offsets, r.total = self.prim_offsets.data_ptr(), self.total.data_ptr()
+        r.total = self.total.data_ptr()
         r.capacity, r.id_cap = self.capacity, self.id_cap
         return r
 
@@ -91,7 +89,7 @@ class HitRecord:
         return self._usable
 
     def nbytes(self) -> int:
-        return self.ids.numel() * 4 + self.ray_offsets.numel() * 8 + self.prim_offsets.numel() * 4
+        return self.ids.numel() * 4 + self.ray_offsets.numel() * 8
 
     def lists(self):
         """Python view for tests: list of per-ray id arrays (host)."""

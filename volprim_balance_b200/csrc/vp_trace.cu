@@ -151,7 +151,10 @@ __device__ __forceinline__ bool fast_isect(const DevScene &S, int pos, float3 o,
     float ba = __fdividef(b, a);
     float lx = fmaf(ba, dd.x, oo.x), ly = fmaf(ba, dd.y, oo.y), lz = fmaf(ba, dd.z, oo.z);
     float discr = 1.f - (lx * lx + ly * ly + lz * lz);
-    if (!(discr >= -2e-4f) || !(a > 0.f)) return false;
+    // |l|^2 is the small difference of terms of size |o'|^2: its rounding error grows like eps |o'| (a 0.0015-unit
+    // primitive seen from 4 units away has |o'| ~ 2700, error ~ 4e-3).  The margin follows it, so that a grazing hit is
+    // never lost here; false candidates cost one exact test in the drain.
+    if (!(discr >= -(2e-4f + 2e-6f * (fabsf(oo.x) + fabsf(oo.y) + fabsf(oo.z)))) || !(a > 0.f)) return false;
     float sq = sqrtf(a * fmaxf(discr, 0.f));
     float q = b + copysignf(sq, b);
     float x0 = __fdividef(c, q), x1 = __fdividef(q, a);
@@ -955,6 +958,64 @@ __device__ __forceinline__ RfEval rf_eval(float3 o, float3 d, float4 g0, float4 
     return e;
 }
 
+// quat_to_matrix / R^T v with fused multiply-adds (value paths of the adjoint; nothing here decides hit order)
+__device__ __forceinline__ Mat3 quat_to_matrix_fast(float4 q)
+{
+    const float x = q.x, y = q.y, z = q.z, w = q.w;
+    Mat3 R;
+    R.m[0][0] = 1.f - 2.f * fmaf(y, y, z * z);
+    R.m[0][1] = 2.f * fmaf(x, y, -z * w);
+    R.m[0][2] = 2.f * fmaf(x, z, y * w);
+    R.m[1][0] = 2.f * fmaf(x, y, z * w);
+    R.m[1][1] = 1.f - 2.f * fmaf(x, x, z * z);
+    R.m[1][2] = 2.f * fmaf(y, z, -x * w);
+    R.m[2][0] = 2.f * fmaf(x, z, -y * w);
+    R.m[2][1] = 2.f * fmaf(y, z, x * w);
+    R.m[2][2] = 1.f - 2.f * fmaf(x, x, y * y);
+    return R;
+}
+__device__ __forceinline__ float3 rot_t_mul_fast(const Mat3 &R, float3 v)
+{
+    return make_float3(fmaf(R.m[2][0], v.z, fmaf(R.m[1][0], v.y, R.m[0][0] * v.x)),
+                       fmaf(R.m[2][1], v.z, fmaf(R.m[1][1], v.y, R.m[0][1] * v.x)),
+                       fmaf(R.m[2][2], v.z, fmaf(R.m[1][2], v.y, R.m[0][2] * v.x)));
+}
+
+// eval_transmission from an origin that may be FAR from the primitive (the gather adjoint evaluates every hit from the
+// ray's original origin: no per-hit origin has to be carried from the ray-major to the primitive-major pass).  From
+// |o - c| / s ~ 1e3 the peak parameter t* = -(o'.d') / (d'.d') loses its low bits and p* slides ALONG the ray by up to
+// ~1e-6 -- invisible in G (stationary in t) but first order in the gradient terms.  So the origin is first moved to the
+// coarse peak (rounded to the world-coordinate grid, exactly like the reference's own re-based origins) and the peak is
+// solved again from there, where |o - c| / s <= extent and fp32 is accurate.
+template <int KERNEL>
+__device__ __forceinline__ RfEval rf_eval_far(float3 o, float3 d, float4 g0, float4 g1, const Mat3 &R)
+{
+    RfEval e;
+    const float isx = 1.f / g1.x, isy = 1.f / g1.y, isz = 1.f / g1.z;
+    const float3 rd = rot_t_mul_fast(R, d);
+    const float3 dd = make_float3(rd.x * isx, rd.y * isy, rd.z * isz);
+    const float inv_dd2 = 1.f / fmaf(dd.x, dd.x, fmaf(dd.y, dd.y, dd.z * dd.z));
+    float3 ro = rot_t_mul_fast(R, make_float3(o.x - g0.x, o.y - g0.y, o.z - g0.z));
+    const float t0 = -fmaf(ro.x * isx, dd.x, fmaf(ro.y * isy, dd.y, ro.z * isz * dd.z)) * inv_dd2;
+    const float3 o1 = make_float3(fmaf(d.x, t0, o.x), fmaf(d.y, t0, o.y), fmaf(d.z, t0, o.z));
+    ro = rot_t_mul_fast(R, make_float3(o1.x - g0.x, o1.y - g0.y, o1.z - g0.z));
+    const float t1 = -fmaf(ro.x * isx, dd.x, fmaf(ro.y * isy, dd.y, ro.z * isz * dd.z)) * inv_dd2;
+    e.pp = make_float3(fmaf(d.x, t1, o1.x), fmaf(d.y, t1, o1.y), fmaf(d.z, t1, o1.z));
+    const float3 w = rot_t_mul_fast(R, make_float3(e.pp.x - g0.x, e.pp.y - g0.y, e.pp.z - g0.z));
+    if (KERNEL == VP_KERNEL_GAUSSIAN) {
+        const float ux = w.x * isx, uy = w.y * isy, uz = w.z * isz;
+        e.G = expf(-0.5f * fmaf(ux, ux, fmaf(uy, uy, uz * uz)));
+    } else {
+        const float ux = w.x * isx * (1.f / 3.f), uy = w.y * isy * (1.f / 3.f), uz = w.z * isz * (1.f / 3.f);
+        e.G = fmaxf(0.75f * (1.f - fmaf(ux, ux, fmaf(uy, uy, uz * uz))), 0.f);
+    }
+    e.op = g0.w;
+    float a = e.op * e.G;
+    if (!(a < 0.9999f)) a = 0.9999f;
+    e.T = 1.f - a;
+    return e;
+}
+
 // GaussianKernel.density_integral full range (common.py:199-206, 238-243); returns clamped rho
 __device__ __forceinline__ float gauss_density_integral(float4 g1, const Isect &is)
 {
@@ -1070,34 +1131,49 @@ __device__ __forceinline__ void flush_counters(const Counters &cn, vp_stats *st)
 struct RaySrc {
     const float *o, *d, *maxt, *jitter;
     vp_camera cam;
-    float tan_half;        // tan(fov_x / 2), computed once on the host in double
+    // computed once on the host in double:
+    float tan_half;        // tan(fov_x / 2)
+    float inv_w, inv_h;    // 1 / width, 1 / height
+    float ly_scale;        // tan_half / aspect
     int32_t has_cam, spp;
     int64_t index_base;    // ray i of the call is sample (index_base + i) of the sensor (row bands, record bands)
 };
 
-// One ray of a perspective sensor: sample index gi = pixel * spp + sample, pixel row-major.  Every operation is
-// individually rounded so that the stand-alone ray generation kernel and the fused paths produce identical rays.
+// One ray of a perspective sensor: sample index gi = pixel * spp + sample, pixel row-major.  ONE routine for the
+// stand-alone ray generation kernel and every fused path, so that all of them see bit-identical rays; a sample index
+// below 2^31 (always, for a film) keeps the index arithmetic in 32 bits, and there is no IEEE division on the way --
+// the primitive-major pass of the gather adjoint regenerates a ray per bucket entry.
 __device__ __forceinline__ void camera_ray(const RaySrc &S, int64_t i, float3 &o, float3 &d, float &maxt)
 {
     const vp_camera &cam = S.cam;
     const int64_t gi = S.index_base + i;
-    const int64_t pix = gi / S.spp;
-    const int x = (int)(pix % cam.width), y = (int)(pix / cam.width);
+    int x, y;
+    if (gi < 0x7fffffffll) {
+        const uint32_t pix = (uint32_t)gi / (uint32_t)S.spp;
+        y = (int)(pix / (uint32_t)cam.width);
+        x = (int)(pix - (uint32_t)y * (uint32_t)cam.width);
+    } else {
+        const int64_t pix = gi / S.spp;
+        y = (int)(pix / cam.width);
+        x = (int)(pix - (int64_t)y * cam.width);
+    }
     float jx = 0.5f, jy = 0.5f;
     if (S.jitter) { jx = S.jitter[2 * i]; jy = S.jitter[2 * i + 1]; }
-    const float u = __fdiv_rn(__fadd_rn((float)x, jx), (float)cam.width);
-    const float v = __fdiv_rn(__fadd_rn((float)y, jy), (float)cam.height);
-    const float aspect = __fdiv_rn((float)cam.width, (float)cam.height);
+    const float u = __fmul_rn(__fadd_rn((float)x, jx), S.inv_w);
+    const float v = __fmul_rn(__fadd_rn((float)y, jy), S.inv_h);
     // Mitsuba perspective sensor: +z forward, +x to the LEFT of the image, +y up
     const float lx = __fmul_rn(__fadd_rn(__fsub_rn(1.f, __fmul_rn(2.f, u)), __fmul_rn(2.f, cam.cx)), S.tan_half);
-    const float ly = __fdiv_rn(__fmul_rn(__fadd_rn(__fsub_rn(1.f, __fmul_rn(2.f, v)), __fmul_rn(2.f, cam.cy)), S.tan_half), aspect);
-    const float inv_n = __frcp_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(lx, lx), __fmul_rn(ly, ly)), 1.f)));
+    const float ly = __fmul_rn(__fadd_rn(__fsub_rn(1.f, __fmul_rn(2.f, v)), __fmul_rn(2.f, cam.cy)), S.ly_scale);
+    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(lx, lx), __fmul_rn(ly, ly)), 1.f);
+    float inv_n = rsqrtf(n2);
+    inv_n = __fmul_rn(inv_n, __fsub_rn(1.5f, __fmul_rn(__fmul_rn(0.5f, n2), __fmul_rn(inv_n, inv_n))));   // one Newton step
     const float3 dl = make_float3(__fmul_rn(lx, inv_n), __fmul_rn(ly, inv_n), inv_n);
     const float *m = cam.to_world;
     d = make_float3(__fadd_rn(__fadd_rn(__fmul_rn(m[0], dl.x), __fmul_rn(m[1], dl.y)), __fmul_rn(m[2], dl.z)),
                     __fadd_rn(__fadd_rn(__fmul_rn(m[4], dl.x), __fmul_rn(m[5], dl.y)), __fmul_rn(m[6], dl.z)),
                     __fadd_rn(__fadd_rn(__fmul_rn(m[8], dl.x), __fmul_rn(m[9], dl.y)), __fmul_rn(m[10], dl.z)));
-    const float inv_z = __frcp_rn(dl.z);
+    // 1 / dl.z = sqrt(n2) up to rounding: no division needed
+    const float inv_z = __fmul_rn(n2, inv_n);
     const float near_t = __fmul_rn(cam.near_clip, inv_z), far_t = __fmul_rn(cam.far_clip, inv_z);
     o = make_float3(__fmaf_rn(d.x, near_t, m[3]), __fmaf_rn(d.y, near_t, m[7]), __fmaf_rn(d.z, near_t, m[11]));
     maxt = __fsub_rn(far_t, near_t);
@@ -1105,7 +1181,9 @@ __device__ __forceinline__ void camera_ray(const RaySrc &S, int64_t i, float3 &o
 
 __device__ __forceinline__ void load_ray(const RaySrc &S, int64_t r, float3 &o, float3 &d, float &maxt)
 {
+#ifndef VP_NO_CAMERA
     if (S.has_cam) { camera_ray(S, r, o, d, maxt); return; }
+#endif
     o = make_float3(S.o[3 * r], S.o[3 * r + 1], S.o[3 * r + 2]);
     d = make_float3(S.d[3 * r], S.d[3 * r + 1], S.d[3 * r + 2]);
     maxt = S.maxt ? S.maxt[r] : FLT_MAX;
@@ -1113,11 +1191,11 @@ __device__ __forceinline__ void load_ray(const RaySrc &S, int64_t r, float3 &o, 
 
 // per-hit state the ray-major pass of the gather adjoint leaves in the bucket of the hit primitive
 struct GatherBuf {
-    const uint32_t *prim_offsets;   // [N + 1] bucket starts (exclusive prefix of the recorded hit counts)
-    uint32_t *cursor;               // [N] entries written so far
-    float4 *state;                  // (dcol.rgb, dalpha)
-    uint32_t *ray;                  // ray index of the entry
-    const int64_t *total;           // record validity: total[0] <= capacity && total[1] == 0
+    const uint32_t *offsets;   // [N + 1] bucket starts (exclusive prefix of the recorded hits per primitive)
+    const uint32_t *rank;      // [capacity] position of record entry e inside the bucket of its primitive
+    float4 *state;             // (dcol.rgb, dalpha) per bucket slot
+    uint32_t *ray;             // ray index per bucket slot; 0xFFFFFFFF = nothing written (ray skipped, zero gradient)
+    const int64_t *total;      // record validity: total[0] <= capacity && total[1] == 0
     int64_t capacity;
 };
 
@@ -1129,7 +1207,6 @@ struct TraceArgs {
     int32_t *ids;            // forward: hit-id output (dense, strides rs / hs)
     int32_t cap;
     int64_t rs, hs;
-    uint32_t *prim_counts;   // forward, optional: recorded hits per primitive (original numbering)
     // adjoint
     const float *dL, *state_in;
     const int32_t *rec_ids;       // replay: dense (rs, hs, rec_counts, cap) or compressed rows (rec_offsets, stride 1)
@@ -1186,10 +1263,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
             T = expf(-rho * g0.w);                      // tomo:44
         }
         beta *= T;                                      // rf:146 / tomo:85
-        if (A.ids && depth < (uint32_t)A.cap) {
-            A.ids[r * A.rs + depth * A.hs] = __float_as_int(g1.w);
-            if (A.prim_counts) atomicAdd(A.prim_counts + __float_as_int(g1.w), 1u);   // bucket sizes of the gather adjoint
-        }
+        // (no atomics in this kernel: a RED anywhere in the hit loop -- even one that never executes -- stops ptxas from
+        // moving the loads of the drain across it and doubled the kernel's time; per-primitive hit counts are taken from
+        // the compressed record in a flat pass of the adjoint instead)
+        if (A.ids && depth < (uint32_t)A.cap) A.ids[r * A.rs + depth * A.hs] = __float_as_int(g1.w);
         // ray.o = si.p + ray.d * 1e-4                     rf:149 / tomo:114
         o.x = fmaf(d.x, P.eps_advance, fmaf(d.x, is.tn, o.x));
         o.y = fmaf(d.y, P.eps_advance, fmaf(d.y, is.tn, o.y));
@@ -1197,6 +1274,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
         depth += 1;
         cn.hits++;
         if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) return false;  // rf:173-174
+#ifndef VP_NO_RR
         if (INTEG == VP_INTEGRATOR_RF && P.use_rr) {                          // rf:177-183 (primal pass only)
             const float rr_prob = fmaxf(beta, 0.1f);
             if (depth >= P.rr_depth && beta < 0.1f) {
@@ -1206,6 +1284,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
                 if (!(u < rr_prob)) return false;
             }
         }
+#endif
         if (!(depth < P.max_depth)) return false;                             // rf:186
         return true;
     };
@@ -1264,13 +1343,15 @@ struct RfCoeffs {
     float dcol[3];    // d loss / d colour, zero where the colour is clamped at 0
 };
 
-template <int KERNEL, int D>
+template <int KERNEL, int D, bool FAR = false>
 __device__ __forceinline__ RfCoeffs rf_adjoint_coeffs(const DevScene &S, int pos, float3 o, float3 d, float4 g0, float4 g1,
                                                       const Mat3 &Rm, const Isect &is, float beta, const float (&g)[3],
                                                       float (&L)[3], const float (&Y)[(D >= 0) ? (D + 1) * (D + 1) : 1])
 {
     RfCoeffs c;
-    RfEval e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
+    RfEval e;
+    if constexpr (FAR) e = rf_eval_far<KERNEL>(o, d, g0, g1, Rm);
+    else e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
     float raw[3] = { 0.f, 0.f, 0.f };
     if constexpr (D >= 0) sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw);
     const float omt = 1.f - e.T;
@@ -1366,12 +1447,13 @@ __device__ __forceinline__ void rf_scatter_hit(const TraceArgs &A, float4 g0, fl
     }
 }
 
-// gather formulation, ray-major pass: the per-hit coefficients go to the bucket of the hit primitive
-__device__ __forceinline__ void rf_bucket_hit(const TraceArgs &A, int orig, int64_t r, RfCoeffs c)
+// gather formulation, ray-major pass: the per-hit coefficients go to the bucket of the hit primitive, at the slot the
+// counting pass assigned to this record entry (no atomics here: they would pin the loads of the replay loop in place)
+__device__ __forceinline__ void rf_bucket_hit(const TraceArgs &A, int orig, int64_t r, int64_t entry, RfCoeffs c)
 {
     if (!(c.op * c.G < 0.9999f)) c.dalpha = 0.f;      // clamped alpha: no gradient to opacity / geometry
     if (c.dalpha == 0.f && c.dcol[0] == 0.f && c.dcol[1] == 0.f && c.dcol[2] == 0.f) return;
-    const uint32_t slot = __ldg(A.gb.prim_offsets + orig) + atomicAdd(A.gb.cursor + orig, 1u);
+    const uint32_t slot = __ldg(A.gb.offsets + orig) + __ldg(A.gb.rank + entry);
     A.gb.state[slot] = make_float4(c.dcol[0], c.dcol[1], c.dcol[2], c.dalpha);
     A.gb.ray[slot] = (uint32_t)r;
 }
@@ -1494,19 +1576,24 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE != ADJ_WALK ? VP_REPLAY_BL
     if constexpr (INTEG == VP_INTEGRATOR_RF && D >= 0) sh_basis<(D >= 0 ? D : 0)>(d, Y);
     else Y[0] = 0.f;
 
+    int64_t entry = 0;        // index of the current hit in the compressed record (bucket mode)
     auto interact = [&](int pos, float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is) -> bool {
         float T;
         if constexpr (INTEG == VP_INTEGRATOR_RF) {
-            const RfCoeffs c = rf_adjoint_coeffs<KERNEL, D>(S, pos, o, d, g0, g1, Rm, is, beta, g, L, Y);
-            if constexpr (MODE == ADJ_REPLAY_BUCKET) rf_bucket_hit(A, __float_as_int(g1.w), r, c);
+            // bucket mode evaluates every hit from the ray's ORIGINAL origin (rf_eval_far): no exact entry distance, no
+            // origin advance -- the list already fixes which primitives are hit and in which order
+            const RfCoeffs c = rf_adjoint_coeffs<KERNEL, D, MODE == ADJ_REPLAY_BUCKET>(S, pos, o, d, g0, g1, Rm, is, beta, g, L, Y);
+            if constexpr (MODE == ADJ_REPLAY_BUCKET) rf_bucket_hit(A, __float_as_int(g1.w), r, entry, c);
             else rf_scatter_hit<KERNEL, D>(A, g0, g1, g2, Rm, c, Y);
             T = c.T;
         } else
             T = tomo_adjoint_hit<KERNEL>(S, A, o, d, g0, g1, g2, Rm, is, g, L);
         beta *= T;
-        o.x = fmaf(d.x, P.eps_advance, fmaf(d.x, is.tn, o.x));
-        o.y = fmaf(d.y, P.eps_advance, fmaf(d.y, is.tn, o.y));
-        o.z = fmaf(d.z, P.eps_advance, fmaf(d.z, is.tn, o.z));
+        if constexpr (MODE != ADJ_REPLAY_BUCKET) {
+            o.x = fmaf(d.x, P.eps_advance, fmaf(d.x, is.tn, o.x));
+            o.y = fmaf(d.y, P.eps_advance, fmaf(d.y, is.tn, o.y));
+            o.z = fmaf(d.z, P.eps_advance, fmaf(d.z, is.tn, o.z));
+        }
         depth += 1;
         cn.hits++;
         if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) return false;
@@ -1530,6 +1617,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE != ADJ_WALK ? VP_REPLAY_BL
                 list = A.rec_ids + b;
                 stride = 1;
                 n = (uint32_t)(A.rec_offsets[r + 1] - b);
+                entry = b;
             }
             // software pipeline: the id -> position -> records chain of hit k+1 is started during hit k
             int orig_next = n > 0 ? list[0] : -1;
@@ -1543,9 +1631,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE != ADJ_WALK ? VP_REPLAY_BL
                 pos_next = orig_next >= 0 ? __ldg(S.inv_perm + orig_next) : 0;
                 if (orig_next >= 0) prefetch_prim(S, pos_next);
                 float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
-                Mat3 Rm = vp_quat_to_matrix_rn(g2);
-                Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
-                interact(pos, g0, g1, g2, Rm, is);
+                if constexpr (MODE == ADJ_REPLAY_BUCKET) {
+                    const Mat3 Rm = quat_to_matrix_fast(g2);
+                    Isect is;
+                    is.valid = true; is.tn = is.tf = 0.f;
+                    is.ro = is.rd = make_float3(0.f, 0.f, 0.f);
+                    interact(pos, g0, g1, g2, Rm, is);
+                } else {
+                    Mat3 Rm = vp_quat_to_matrix_rn(g2);
+                    Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
+                    interact(pos, g0, g1, g2, Rm, is);
+                }
+                ++entry;
             }
         }
     } else {
@@ -1568,11 +1665,26 @@ struct GatherArgs {
     const float *data10, *attr;     // the primitives in the reference layouts (context copies, original order)
     GatherBuf gb;
     int64_t p_begin, p_end;
+    const uint32_t *extra_items;    // EXTRA pass: primitive of every extra work item
+    const uint32_t *extra_offsets;  // [N + 1] exclusive prefix of the extra items per primitive
+    const uint32_t *n_extra;        // device scalar: number of extra items
     float *g_data, *g_attr, *g_sh;
 };
 
-template <int KERNEL, int D>
-__global__ void __launch_bounds__(128, 4) k_adjoint_gather(GatherArgs A)
+#ifndef VP_GATHER_CHUNK
+#define VP_GATHER_CHUNK 256        // bucket entries one warp accumulates (8 rounds of 32 lanes)
+#endif
+constexpr uint32_t GATHER_CHUNK = VP_GATHER_CHUNK;
+
+// Buckets are heavy-tailed (a primitive close to the camera collects tens of thousands of hits, the median one a few
+// dozen): a warp takes at most GATHER_CHUNK entries.  The MAIN pass (EXTRA = false) gives every primitive of the
+// range one warp for its first chunk and adds the sums with plain read-modify-writes; the EXTRA pass runs one warp per
+// further chunk of the big buckets and adds with reductions (few: 59 per 256 hits instead of 27 per hit).
+#ifndef VP_GATHER_BLOCKS
+#define VP_GATHER_BLOCKS 5
+#endif
+template <int KERNEL, int D, bool EXTRA>
+__global__ void __launch_bounds__(128, VP_GATHER_BLOCKS) k_adjoint_gather(GatherArgs A)
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int NB = (D >= 0) ? (D + 1) * (D + 1) : 0;
@@ -1581,16 +1693,31 @@ __global__ void __launch_bounds__(128, 4) k_adjoint_gather(GatherArgs A)
     constexpr int M = NV / 32;                      // finished sums per lane
     static_assert(C + 16 <= 64, "SH degree 3 at most");
     const int lane = threadIdx.x & 31;
-    const int64_t p = A.p_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (p >= A.p_end || !record_usable(A.gb)) return;
-    const uint32_t cnt = A.gb.cursor[p];
-    if (cnt == 0) return;
-    const uint32_t base = __ldg(A.gb.prim_offsets + p);
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (!record_usable(A.gb)) return;
+    int64_t p;
+    uint32_t first;        // first bucket entry of this warp's chunk
+    if constexpr (EXTRA) {
+        if (w >= (int64_t)__ldg(A.n_extra)) return;
+        p = __ldg(A.extra_items + w);
+        if (p < A.p_begin || p >= A.p_end) return;
+        first = ((uint32_t)w - __ldg(A.extra_offsets + p) + 1u) * GATHER_CHUNK;
+    } else {
+        p = A.p_begin + w;
+        if (p >= A.p_end) return;
+        first = 0;
+    }
+    const uint32_t base = __ldg(A.gb.offsets + p);
+    const uint32_t size = __ldg(A.gb.offsets + p + 1) - base;
+    if (first >= size) return;
+    const uint32_t cnt = min(size - first, GATHER_CHUNK);
+    const float4 *bstate = A.gb.state + base + first;
+    const uint32_t *bray = A.gb.ray + base + first;
     const float *rec = A.data10 + 10 * p;
     const float4 g0 = make_float4(__ldg(rec), __ldg(rec + 1), __ldg(rec + 2), A.attr ? __ldg(A.attr + p) : 1.f);
     const float4 g1 = make_float4(__ldg(rec + 3), __ldg(rec + 4), __ldg(rec + 5), 0.f);
     const float4 g2 = make_float4(__ldg(rec + 6), __ldg(rec + 7), __ldg(rec + 8), __ldg(rec + 9));
-    const Mat3 Rm = vp_quat_to_matrix_rn(g2);
+    const Mat3 Rm = quat_to_matrix_fast(g2);
     float acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.f;
@@ -1598,13 +1725,16 @@ __global__ void __launch_bounds__(128, 4) k_adjoint_gather(GatherArgs A)
     // one entry ahead: the bucket entry of the next round is in flight while this one is evaluated
     uint32_t i = lane;
     float4 st_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t ray_next = 0;
-    if (i < cnt) { st_next = __ldcs(A.gb.state + base + i); ray_next = __ldcs(A.gb.ray + base + i); }
+    uint32_t ray_next = 0xffffffffu;
+    if (i < cnt) { ray_next = __ldcs(bray + i); st_next = __ldcs(bstate + i); }
+    bool any = false;
     while (i < cnt) {
         const float4 st = st_next;
         const uint32_t r = ray_next;
         i += 32;
-        if (i < cnt) { st_next = __ldcs(A.gb.state + base + i); ray_next = __ldcs(A.gb.ray + base + i); }
+        if (i < cnt) { ray_next = __ldcs(bray + i); st_next = __ldcs(bstate + i); }
+        if (r == 0xffffffffu) continue;             // slot never written: the ray was skipped or the hit carries no gradient
+        any = true;
         float3 o, d;
         float maxt;
         load_ray(A.src, r, o, d, maxt);
@@ -1621,19 +1751,15 @@ __global__ void __launch_bounds__(128, 4) k_adjoint_gather(GatherArgs A)
             }
         }
         if (st.w != 0.f) {
-            Isect is;
-            is.valid = true; is.tn = is.tf = 0.f;
-            is.rd = vp_rot_t_mul_rn(Rm, d);
-            is.ro = vp_rot_t_mul_rn(Rm, make_float3(o.x - g0.x, o.y - g0.y, o.z - g0.z));
-            const RfEval e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
+            const RfEval e = rf_eval_far<KERNEL>(o, d, g0, g1, Rm);
             acc[C] = fmaf(st.w, e.G, acc[C]);                       // d opacity
-            float3 v, w;
+            float3 v, wv;
             float dw[3];
-            if (rf_geo_terms<KERNEL>(g0, g1, Rm, e.pp, e.G, e.op, st.w, v, w, dw)) {
+            if (rf_geo_terms<KERNEL>(g0, g1, Rm, e.pp, e.G, e.op, st.w, v, wv, dw)) {
                 acc[C + 1] += dw[0]; acc[C + 2] += dw[1]; acc[C + 3] += dw[2];
-                acc[C + 4] = fmaf(w.x, dw[0], acc[C + 4]);
-                acc[C + 5] = fmaf(w.y, dw[1], acc[C + 5]);
-                acc[C + 6] = fmaf(w.z, dw[2], acc[C + 6]);
+                acc[C + 4] = fmaf(wv.x, dw[0], acc[C + 4]);
+                acc[C + 5] = fmaf(wv.y, dw[1], acc[C + 5]);
+                acc[C + 6] = fmaf(wv.z, dw[2], acc[C + 6]);
                 const float va[3] = { v.x, v.y, v.z };
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
@@ -1642,6 +1768,7 @@ __global__ void __launch_bounds__(128, 4) k_adjoint_gather(GatherArgs A)
             }
         }
     }
+    if (!__any_sync(FULL, any)) return;
     // butterfly reduce-scatter: after the step with lane distance s, a lane holds the partial sums of the half of the
     // index range selected by its bit s; in the end lane l owns indices M * l .. M * l + M - 1
 #pragma unroll
@@ -1654,14 +1781,17 @@ __global__ void __launch_bounds__(128, 4) k_adjoint_gather(GatherArgs A)
             acc[k] = keep + __shfl_xor_sync(FULL, send, sft);
         }
     }
-    // colour coefficients: coalesced read-modify-write
+    // colour coefficients: coalesced read-modify-write (main pass) / reductions (extra chunks of a big bucket)
     if constexpr (C > 0) {
         if (A.g_sh) {
             float *dst = A.g_sh + (size_t)p * C;
 #pragma unroll
             for (int k = 0; k < M; ++k) {
                 const int idx = M * lane + k;
-                if (idx < C) dst[idx] += acc[k];
+                if (idx < C) {
+                    if constexpr (EXTRA) atomicAdd(dst + idx, acc[k]);
+                    else dst[idx] += acc[k];
+                }
             }
         }
     }
@@ -1670,7 +1800,6 @@ __global__ void __launch_bounds__(128, 4) k_adjoint_gather(GatherArgs A)
 #pragma unroll
     for (int j = 0; j < 16; ++j) gs[j] = __shfl_sync(FULL, acc[(C + j) % M], (C + j) / M);
     if (lane == 0) {
-        A.g_attr[p] += gs[0];
         float g10[10];
         float dR[3][3];
 #pragma unroll
@@ -1686,9 +1815,55 @@ __global__ void __launch_bounds__(128, 4) k_adjoint_gather(GatherArgs A)
         chain_dR_to_quat(g2, dR, gq);
         g10[6] = gq[0]; g10[7] = gq[1]; g10[8] = gq[2]; g10[9] = gq[3];
         float *dst = A.g_data + 10 * p;
+        if constexpr (EXTRA) {
+            atomicAdd(A.g_attr + p, gs[0]);
 #pragma unroll
-        for (int k = 0; k < 10; ++k) dst[k] += g10[k];
+            for (int k = 0; k < 10; ++k) atomicAdd(dst + k, g10[k]);
+        } else {
+            A.g_attr[p] += gs[0];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) dst[k] += g10[k];
+        }
     }
+}
+
+// counting pass of the gather adjoint: one thread per record entry; rank[e] = position of the entry inside the bucket
+// of its primitive (arrival order), counts[p] = bucket size.  Flat and coalesced; the only atomics of the adjoint.
+__global__ void __launch_bounds__(256) k_bucket_ranks(const int32_t *__restrict__ ids, const int64_t *__restrict__ total,
+                                                      int64_t capacity, uint32_t *__restrict__ counts, uint32_t *__restrict__ rank)
+{
+    const int64_t n = total[0];
+    if (n > capacity || total[1] != 0) return;
+    // four entries per thread and round: the atomics return a value, so their latency is hidden by having several in flight
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += 4 * stride) {
+        int32_t id[4];
+        uint32_t rk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) id[k] = e0 + k * stride < n ? __ldcs(ids + e0 + k * stride) : -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rk[k] = id[k] >= 0 ? atomicAdd(counts + id[k], 1u) : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (id[k] >= 0) rank[e0 + k * stride] = rk[k];
+    }
+}
+
+// extra work items of the primitive-major pass: ceil(size / CHUNK) - 1 per bucket
+__global__ void k_extra_counts(const uint32_t *__restrict__ offsets, int64_t n, uint32_t *__restrict__ extra)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t c = offsets[p + 1] - offsets[p];
+    extra[p] = c > GATHER_CHUNK ? (c - 1) / GATHER_CHUNK : 0u;
+}
+
+__global__ void k_extra_items(const uint32_t *__restrict__ extra_offsets, int64_t n, uint32_t *__restrict__ items, uint32_t max_items)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t a = extra_offsets[p], b = extra_offsets[p + 1];
+    for (uint32_t k = a; k < b && k < max_items; ++k) items[k] = (uint32_t)p;
 }
 
 // ---- hit records: dense hit-major scratch -> compressed rows ----------------------------------------------------------
@@ -1707,17 +1882,32 @@ __global__ void k_record_counts(const uint32_t *__restrict__ nhits, int64_t n, i
     if (m && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)(total + 1), (unsigned long long)__popc(m));
 }
 
-// one thread per ray: its column of the dense block goes to ids[offset ..).  Reads are coalesced across the warp
-// (same hit index, neighbouring rays); each thread writes its own contiguous row.
-__global__ void k_compact_hits(const int32_t *__restrict__ dense, int64_t n, const uint32_t *__restrict__ counts,
-                               const int64_t *__restrict__ offsets, int32_t *__restrict__ ids, int64_t capacity)
+// Dense hit-major block -> compressed rows.  One warp per 32 consecutive rays; the block is read coalesced (lane = ray,
+// same hit index), transposed through shared memory, and every ray's row is written coalesced (lane = hit index).
+__global__ void __launch_bounds__(128) k_compact_hits(const int32_t *__restrict__ dense, int64_t n, const uint32_t *__restrict__ counts,
+                                                      const int64_t *__restrict__ offsets, int32_t *__restrict__ ids, int64_t capacity)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const uint32_t c = counts[r];
-    const int64_t off = offsets[r];
-    if (off + c > capacity) return;                  // does not fit: total[0] tells the caller
-    for (uint32_t k = 0; k < c; ++k) ids[off + k] = dense[(int64_t)k * n + r];
+    __shared__ int32_t tile[4][32][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t r0 = ((int64_t)blockIdx.x * 4 + wid) * 32;
+    if (r0 >= n) return;
+    const int64_t r = r0 + lane;
+    const uint32_t c = r < n ? counts[r] : 0u;
+    const int64_t off = r < n ? offsets[r] : 0;
+    const uint32_t cmax = __reduce_max_sync(0xffffffffu, c);
+    for (uint32_t k0 = 0; k0 < cmax; k0 += 32) {
+        // rows k0 .. k0 + 31 of the dense block, columns r0 .. r0 + 31
+        const uint32_t kn = min(32u, cmax - k0);
+        for (uint32_t k = 0; k < kn; ++k)
+            tile[wid][k][lane] = (k0 + k < c) ? dense[(int64_t)(k0 + k) * n + r] : -1;
+        __syncwarp();
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t cj = __shfl_sync(0xffffffffu, c, j);
+            const int64_t oj = __shfl_sync(0xffffffffu, off, j);
+            if (k0 + lane < cj && oj + cj <= capacity) ids[oj + k0 + lane] = tile[wid][lane][j];
+        }
+        __syncwarp();
+    }
 }
 
 __global__ void k_raygen(RaySrc S, int64_t total, float *__restrict__ ro, float *__restrict__ rd, float *__restrict__ rmaxt)
@@ -1756,25 +1946,26 @@ void launch_adjoint(const DevScene &S, const vp_params &P, const TraceArgs &A, c
 }
 
 template <int INTEG, int KERNEL, int D>
-void launch_gather(const GatherArgs &G, cudaStream_t st)
+void launch_gather(const GatherArgs &G, int64_t max_extra, cudaStream_t st)
 {
     if constexpr (INTEG == VP_INTEGRATOR_RF) {
         const int64_t warps = G.p_end - G.p_begin;
         if (warps <= 0) return;
-        const int64_t blocks = (warps * 32 + 127) / 128;
-        k_adjoint_gather<KERNEL, D><<<(unsigned)blocks, 128, 0, st>>>(G);
+        k_adjoint_gather<KERNEL, D, false><<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(G);
+        if (max_extra > 0) k_adjoint_gather<KERNEL, D, true><<<(unsigned)((max_extra * 32 + 127) / 128), 128, 0, st>>>(G);
     }
 }
 
 // WHAT: 0 = forward, 1 = adjoint (ray-major), 2 = gather (primitive-major pass of the rf adjoint)
 template <int WHAT>
-int dispatch(vp_ctx *ctx, const DevScene &S, const vp_params &P, const TraceArgs &A, const GatherArgs *G, cudaStream_t st)
+int dispatch(vp_ctx *ctx, const DevScene &S, const vp_params &P, const TraceArgs &A, const GatherArgs *G, cudaStream_t st,
+             int64_t max_extra = 0)
 {
 #define VP_LAUNCH(I, K, D)                                        \
     do {                                                          \
         if (WHAT == 0) launch_forward<I, K, D>(S, P, A, st);      \
         else if (WHAT == 1) launch_adjoint<I, K, D>(S, P, A, st); \
-        else launch_gather<I, K, D>(*G, st);                      \
+        else launch_gather<I, K, D>(*G, max_extra, st);           \
         return VP_OK;                                             \
     } while (0)
     const bool gauss = P.kernel == VP_KERNEL_GAUSSIAN;
@@ -1836,7 +2027,11 @@ int make_ray_src(vp_ctx *ctx, const vp_ray_source *rs, int64_t R, RaySrc &out, i
         if (R != (int64_t)c.width * rows * rs->spp)
             return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": n_rays must equal width * rows * spp of the sensor");
         out.cam = c;
-        out.tan_half = (float)std::tan((double)c.fov_x_deg * 0.5 * 0.017453292519943295);
+        const double th = std::tan((double)c.fov_x_deg * 0.5 * 0.017453292519943295);
+        out.tan_half = (float)th;
+        out.inv_w = (float)(1.0 / c.width);
+        out.inv_h = (float)(1.0 / c.height);
+        out.ly_scale = (float)(th * (double)c.height / (double)c.width);
         out.has_cam = 1;
         out.spp = rs->spp;
         out.jitter = rs->jitter;
@@ -1866,8 +2061,8 @@ RaySrc slice_ray_src(const RaySrc &s, int64_t first)
 
 int check_record(vp_ctx *ctx, const vp_hit_record *rec, const char *who)
 {
-    if (!rec->ray_offsets || !rec->ids || !rec->prim_offsets || !rec->total)
-        return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record arrays (ray_offsets, ids, prim_offsets, total) are required");
+    if (!rec->ray_offsets || !rec->ids || !rec->total)
+        return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record arrays (ray_offsets, ids, total) are required");
     if (rec->capacity <= 0 || rec->capacity >= (1ll << 32) || rec->id_cap <= 0)
         return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record needs 0 < capacity < 2^32 and id_cap > 0");
     return VP_OK;
@@ -1972,9 +2167,7 @@ int vp_render_forward_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sour
         return VP_OK;
     }
     // ---- recording: row bands bound the dense hit-major scratch ----
-    const int64_t n = ctx->n;
     VP_CUDA_CHECK(ctx, cudaMemsetAsync(rec->total, 0, 2 * sizeof(int64_t), st));
-    VP_CUDA_CHECK(ctx, cudaMemsetAsync(rec->prim_offsets, 0, sizeof(uint32_t) * (size_t)(n + 1), st));
     if (R == 0) {
         VP_CUDA_CHECK(ctx, cudaMemsetAsync(rec->ray_offsets, 0, sizeof(int64_t), st));
         return VP_OK;
@@ -1996,7 +2189,7 @@ int vp_render_forward_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sour
     }
     if ((rc = vp_ensure(ctx, ctx->rec_dense, sizeof(int32_t) * (size_t)cap * (size_t)band))) return rc;
     if ((rc = vp_ensure(ctx, ctx->rec_counts, sizeof(uint32_t) * (size_t)band))) return rc;
-    if ((rc = vp_ensure(ctx, ctx->scan_tmp, sizeof(uint64_t) * (size_t)(vpscan::n_tiles(band > n ? band : n) + 1)))) return rc;
+    if ((rc = vp_ensure(ctx, ctx->scan_tmp, sizeof(uint64_t) * (size_t)(vpscan::n_tiles(band) + 1)))) return rc;
     uint32_t *nh_all = nhits;
     if (!nh_all) {
         if ((rc = vp_ensure(ctx, ctx->rec_nhits, sizeof(uint32_t) * (size_t)R))) return rc;
@@ -2020,21 +2213,17 @@ int vp_render_forward_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sour
         B.T = T ? T + first : nullptr;
         B.nhits = nh_all + first;
         B.ids = (int32_t *)ctx->rec_dense.ptr; B.cap = cap; B.rs = 1; B.hs = cnt;
-        B.prim_counts = rec->prim_offsets;
         if ((rc = dispatch<0>(ctx, S, Pb, B, nullptr, st))) return rc;
-        const unsigned blocks = (unsigned)((cnt + 255) / 256);
+        const unsigned blocks = (unsigned)((cnt + 255) / 256), cblocks = (unsigned)((cnt + 127) / 128);
         k_record_counts<<<blocks, 256, 0, st>>>(B.nhits, cnt, cap, (uint32_t *)ctx->rec_counts.ptr, rec->total);
         vpscan::exclusive_scan<unsigned long long>((const uint32_t *)ctx->rec_counts.ptr, cnt,
                                                    (unsigned long long *)rec->ray_offsets + first,
                                                    (unsigned long long *)ctx->scan_tmp.ptr, (unsigned long long *)rec->total,
                                                    (unsigned long long *)rec->ray_offsets + first + cnt, st);
-        k_compact_hits<<<blocks, 256, 0, st>>>((const int32_t *)ctx->rec_dense.ptr, cnt, (const uint32_t *)ctx->rec_counts.ptr,
+        k_compact_hits<<<cblocks, 128, 0, st>>>((const int32_t *)ctx->rec_dense.ptr, cnt, (const uint32_t *)ctx->rec_counts.ptr,
                                                rec->ray_offsets + first, rec->ids, rec->capacity);
         first += cnt;
     }
-    // per-primitive hit counts -> bucket offsets (in place; [n] receives the total)
-    vpscan::exclusive_scan<uint32_t>(rec->prim_offsets, n, rec->prim_offsets, (uint32_t *)ctx->scan_tmp.ptr, nullptr,
-                                     rec->prim_offsets + n, st);
     VP_CUDA_CHECK(ctx, cudaGetLastError());
     return VP_OK;
 }
@@ -2048,7 +2237,10 @@ int adjoint_common(vp_ctx *ctx, const vp_params *p_in, const vp_ray_source *rays
     int iw, ih;
     int rc = make_ray_src(ctx, rays, R, src, iw, ih, who);
     if (rc) return rc;
-    P.image_width = P.image_height = 0;       // the replay passes index rays linearly
+    // the ray-major replay walks the rays in 8x4 pixel tiles like the primal did (neighbouring rays replay the same
+    // primitives: their records and colour blocks are shared through L1); explicit batches are indexed linearly
+    P.image_width = src.has_cam ? iw : 0;
+    P.image_height = src.has_cam ? ih : 0;
     if ((rc = check_common(ctx, &P, R, who))) return rc;
     if (!rec) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": a hit record is required (vp_trace_adjoint re-traces)");
     if ((rc = check_record(ctx, rec, who))) return rc;
@@ -2061,8 +2253,8 @@ int adjoint_common(vp_ctx *ctx, const vp_params *p_in, const vp_ray_source *rays
 GatherBuf gather_buf(vp_ctx *ctx, const vp_hit_record *rec)
 {
     GatherBuf gb;
-    gb.prim_offsets = rec->prim_offsets;
-    gb.cursor = (uint32_t *)ctx->adj_cursor.ptr;
+    gb.offsets = (const uint32_t *)ctx->adj_offsets.ptr;
+    gb.rank = (const uint32_t *)ctx->adj_rank.ptr;
     gb.state = (float4 *)ctx->adj_state.ptr;
     gb.ray = (uint32_t *)ctx->adj_ray.ptr;
     gb.total = rec->total;
@@ -2090,11 +2282,29 @@ int vp_adjoint_begin_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sourc
     A.g_data = g_data; A.g_attr = g_attr; A.g_sh = g_sh;
     A.stats = (vp_stats *)ctx->stats.ptr;
     if (P.integrator == VP_INTEGRATOR_RF) {
+        // counting pass: bucket sizes + the slot of every record entry inside its bucket, bucket offsets, and the
+        // extra work items of the buckets that exceed one warp's chunk
         const int64_t n = ctx->n;
-        if ((rc = vp_ensure(ctx, ctx->adj_cursor, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1)))) return rc;
+        const int64_t max_extra = rec->capacity / GATHER_CHUNK + 1;
+        if ((rc = vp_ensure(ctx, ctx->adj_offsets, sizeof(uint32_t) * (size_t)(n + 1)))) return rc;
+        if ((rc = vp_ensure(ctx, ctx->adj_extra, sizeof(uint32_t) * (size_t)(n + 1)))) return rc;
+        if ((rc = vp_ensure(ctx, ctx->adj_items, sizeof(uint32_t) * (size_t)max_extra))) return rc;
+        if ((rc = vp_ensure(ctx, ctx->adj_rank, sizeof(uint32_t) * (size_t)rec->capacity))) return rc;
         if ((rc = vp_ensure(ctx, ctx->adj_state, sizeof(float4) * (size_t)rec->capacity))) return rc;
         if ((rc = vp_ensure(ctx, ctx->adj_ray, sizeof(uint32_t) * (size_t)rec->capacity))) return rc;
-        VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->adj_cursor.ptr, 0, sizeof(uint32_t) * (size_t)(n > 0 ? n : 1), st));
+        if ((rc = vp_ensure(ctx, ctx->scan_tmp, sizeof(uint64_t) * (size_t)(vpscan::n_tiles(n) + 1)))) return rc;
+        uint32_t *offsets = (uint32_t *)ctx->adj_offsets.ptr, *extra = (uint32_t *)ctx->adj_extra.ptr;
+        VP_CUDA_CHECK(ctx, cudaMemsetAsync(offsets, 0, sizeof(uint32_t) * (size_t)(n + 1), st));
+        VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->adj_ray.ptr, 0xff, sizeof(uint32_t) * (size_t)rec->capacity, st));
+        if (n > 0) {
+            int64_t blocks = (rec->capacity + 255) / 256;
+            if (blocks > 148 * 32) blocks = 148 * 32;
+            k_bucket_ranks<<<(unsigned)blocks, 256, 0, st>>>(rec->ids, rec->total, rec->capacity, offsets, (uint32_t *)ctx->adj_rank.ptr);
+            vpscan::exclusive_scan<uint32_t>(offsets, n, offsets, (uint32_t *)ctx->scan_tmp.ptr, nullptr, offsets + n, st);
+            k_extra_counts<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(offsets, n, extra);
+            vpscan::exclusive_scan<uint32_t>(extra, n, extra, (uint32_t *)ctx->scan_tmp.ptr, nullptr, extra + n, st);
+            k_extra_items<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(extra, n, (uint32_t *)ctx->adj_items.ptr, (uint32_t)max_extra);
+        }
     }
     A.gb = gather_buf(ctx, rec);
     if (R == 0) return VP_OK;
@@ -2112,7 +2322,7 @@ int vp_adjoint_finish_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sour
     if (rc) return rc;
     if (P.integrator != VP_INTEGRATOR_RF) return VP_OK;   // volprim_tomography scattered everything in vp_adjoint_begin
     if (p_begin < 0 || p_end > ctx->n || p_begin > p_end) return vp_fail(ctx, VP_E_INVALID, "vp_adjoint_finish: bad primitive range");
-    if (!ctx->adj_cursor.ptr || !ctx->adj_state.ptr) return vp_fail(ctx, VP_E_STATE, "vp_adjoint_finish: call vp_adjoint_begin first");
+    if (!ctx->adj_offsets.ptr || !ctx->adj_state.ptr) return vp_fail(ctx, VP_E_STATE, "vp_adjoint_finish: call vp_adjoint_begin first");
     if (p_begin == p_end) return VP_OK;
     DevScene S = vp_dev_scene(ctx);
     GatherArgs G = {};
@@ -2121,9 +2331,12 @@ int vp_adjoint_finish_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sour
     G.attr = ctx->have_attr ? (const float *)ctx->raw_attr.ptr : nullptr;
     G.gb = gather_buf(ctx, rec);
     G.p_begin = p_begin; G.p_end = p_end;
+    G.extra_items = (const uint32_t *)ctx->adj_items.ptr;
+    G.extra_offsets = (const uint32_t *)ctx->adj_extra.ptr;
+    G.n_extra = G.extra_offsets + ctx->n;
     G.g_data = g_data; G.g_attr = g_attr; G.g_sh = g_sh;
     TraceArgs A = {};
-    if ((rc = dispatch<2>(ctx, S, P, A, &G, st))) return rc;
+    if ((rc = dispatch<2>(ctx, S, P, A, &G, st, rec->capacity / GATHER_CHUNK + 1))) return rc;
     VP_CUDA_CHECK(ctx, cudaGetLastError());
     return VP_OK;
 }
