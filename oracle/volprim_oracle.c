@@ -371,7 +371,20 @@ static inline void consider(const orc_scene *sc, int64_t j, const REAL o[3], con
     gather(sc, j, &e);
     REAL tn, tf, discr;
     int valid = ray_ellipsoid(o, d, &e, &tn, &tf, &discr);
-    if (FABS(discr) < h->min_abs_discr) h->min_abs_discr = FABS(discr);
+    {
+        /* Fragility of the hit / miss decision, in units of what fp32 WORLD COORDINATES resolve of this discriminant:
+         * the ray origin sits on a grid of 2^-24 |o| per half step, the unit-sphere transform of the primitive magnifies
+         * it by 1 / (extent s_min), and d(discr) = 2 |l| d|l|.  For primitives larger than ~0.01 the unit is 1 (plain
+         * |discr|, as the 1e-4 threshold of the tests assumes); for the 0.0015-unit primitives of the 10M stress cloud
+         * it is ~7: no fp32 intersection routine -- Mitsuba's included -- decides |discr| < 7e-4 reliably there. */
+        double smin = (double)e.s[0] < (double)e.s[1] ? (double)e.s[0] : (double)e.s[1];
+        if ((double)e.s[2] < smin) smin = (double)e.s[2];
+        double omax = 1.0;
+        for (int a = 0; a < 3; ++a) if (fabs((double)o[a]) > omax) omax = fabs((double)o[a]);
+        double res = 8.0 * 5.9604644775390625e-08 * omax / (smin * (double)e.extent);
+        REAL dn = (REAL)(fabs((double)discr) / (res > 1e-4 ? res / 1e-4 : 1.0));
+        if (dn < h->min_abs_discr) h->min_abs_discr = dn;
+    }
     if (!valid) return;
     if (FABS(tn) < h->min_abs_t) h->min_abs_t = FABS(tn);
     if (!(tn > R_(0)) || !(tn <= maxt)) return; /* front face behind origin => culled */

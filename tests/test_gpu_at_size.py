@@ -53,7 +53,10 @@ def _check_at_size(name, sel_fn, id_cap, hits_estimate, max_fragile_frac=5e-3, g
     ids_g, cnt_g = record_lists(rec, sel, id_cap)
     tsel = torch.from_numpy(sel).cuda()
     part = TraceResult(fwd.rgb[tsel], fwd.beta[tsel], fwd.nhits[tsel])
-    out = compare_forward(part, ref, id_cap, max_fragile_frac=max_fragile_frac, replay=(osc, op, o[sel], d[sel], mt[sel]), ids_g=ids_g)
+    ref64 = oracle_scene(cloud, precision="f64").forward(op, o[sel], d[sel], mt[sel], cap=id_cap)
+    out = compare_forward(part, ref, id_cap, max_fragile_frac=max_fragile_frac, replay=(osc, op, o[sel], d[sel], mt[sel]), ids_g=ids_g,
+                          res_orc64=ref64)
+    del ref64
     info = {k: v for k, v in out.items() if k[0] != "_"}
     info.update(primitives=cloud.n, rays=W * H, hits_per_ray=float(nh.mean()), max_hits=int(nh.max()), record_GB=rec.nbytes() / 2**30,
                 entries=entries)

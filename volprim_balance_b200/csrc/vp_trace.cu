@@ -135,7 +135,11 @@ struct Counters {
 // Approximate entry distance from the pre-transformed record xf (rows of M = diag(1/(extent s)) R^T with the
 // centre in .w).  Only used to ORDER candidates and to bin them into intervals; validity is conservative
 // (slightly negative discriminants pass) because the drain phase repeats the test exactly.
-__device__ __forceinline__ bool fast_isect(const DevScene &S, int pos, float3 o, float3 d, float &tn)
+// `o` is the walker origin advanced to the start of the current interval (o0 + t_base d) and the result is shifted back
+// by t_base: seen from the interval start a primitive is tens, not thousands, of its own radii away, so the entry
+// distance resolves the gaps the parity contract asks the hit order to resolve (from 4 units away a grazing entry on a
+// 0.0015-unit primitive was off by > 1e-4 and swapped places with its neighbour).
+__device__ __forceinline__ bool fast_isect(const DevScene &S, int pos, float3 o, float3 d, float t_base, float &tn)
 {
     VP_CHECK(pos >= 0 && pos < S.n, 1, pos, S.n);
     const float4 *x = S.xf + 3ll * pos;
@@ -151,14 +155,15 @@ __device__ __forceinline__ bool fast_isect(const DevScene &S, int pos, float3 o,
     float ba = __fdividef(b, a);
     float lx = fmaf(ba, dd.x, oo.x), ly = fmaf(ba, dd.y, oo.y), lz = fmaf(ba, dd.z, oo.z);
     float discr = 1.f - (lx * lx + ly * ly + lz * lz);
-    // |l|^2 is the small difference of terms of size |o'|^2: its rounding error grows like eps |o'| (a 0.0015-unit
-    // primitive seen from 4 units away has |o'| ~ 2700, error ~ 4e-3).  The margin follows it, so that a grazing hit is
-    // never lost here; false candidates cost one exact test in the drain.
-    if (!(discr >= -(2e-4f + 2e-6f * (fabsf(oo.x) + fabsf(oo.y) + fabsf(oo.z)))) || !(a > 0.f)) return false;
+    // Conservative validity: the interval origin sits on the world-coordinate grid, up to 2^-24 |o| beside the ray, and
+    // the unit-sphere transform of a 0.0015-unit primitive magnifies that 700 times (3e-4 in the discriminant); |l|^2 is
+    // also a small difference of terms of size |o'|^2.  A grazing hit must never be lost here -- false candidates only
+    // cost one exact test in the drain (0.5 % of the candidates have |discr| < 1e-2).
+    if (!(discr >= -(1e-2f + 2e-6f * (fabsf(oo.x) + fabsf(oo.y) + fabsf(oo.z)))) || !(a > 0.f)) return false;
     float sq = sqrtf(a * fmaxf(discr, 0.f));
     float q = b + copysignf(sq, b);
     float x0 = __fdividef(c, q), x1 = __fdividef(q, a);
-    tn = fminf(x0, x1);
+    tn = fminf(x0, x1) + t_base;
     return tn == tn;
 }
 
@@ -288,6 +293,14 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
         const float slack = 1e-4f + 1e-5f * t_start;
         const float t_lo = strict_lo ? t_start : t_start - slack;
         const float delta_floor = fmaxf(delta_min, 2.f * slack);
+        // origin of the ordering tests of this interval (see fast_isect)
+#ifdef VP_ORDER_FAR
+        const float t_base = 0.f;
+        const float3 ob = o0;
+#else
+        const float t_base = fmaxf(t_lo, 0.f);
+        const float3 ob = make_float3(fmaf(d.x, t_base, o0.x), fmaf(d.y, t_base, o0.y), fmaf(d.z, t_base, o0.z));
+#endif
         // (the max keeps the interval from collapsing to nothing when delta is below one ulp of a large t_start)
         float t_end = (S.root >= 0 && !closest_mode) ? fmaxf(t_start + delta, t_start * 1.000001f) : VP_INF;
         int n_c = 0;
@@ -343,7 +356,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
                 if (cnode < 0) {
                     float tn;
                     cn.candidates++;
-                    if (fast_isect(S, ~cnode, o0, d, tn) && tn > t_lo && tn < best_t) {
+                    if (fast_isect(S, ~cnode, ob, d, t_base, tn) && tn > t_lo && tn < best_t) {
                         best_t = tn;
                         best_pos = ~cnode;
                         t_end = tn;  // nothing beyond the closest entry is needed
@@ -375,7 +388,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
                 const int pos = s_id[k * STRIDE];
                 float tn;
                 bool ok;
-                if (S.root >= 0) ok = fast_isect(S, pos, o0, d, tn);
+                if (S.root >= 0) ok = fast_isect(S, pos, ob, d, t_base, tn);
                 else { ok = true; tn = 1.f; }
                 if (ok && tn > t_lo && tn <= t_end) {
                     list_insert<STRIDE>(s_id, s_t, n_h, tn, pos);   // n_h <= k: entry k is already read
@@ -657,6 +670,14 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         if (!am) break;
         const float t_lo = t_start - (1e-4f + 1e-5f * t_start);   // look-back and width floor: see walk_ray
         const float t_end = fmaxf(t_start + delta, t_start * 1.000001f);   // progress even below one ulp of t_start
+        // origin of the ordering tests of this interval (see fast_isect)
+#ifdef VP_ORDER_FAR
+        const float t_base = 0.f;
+        const float3 ob = o0;
+#else
+        const float t_base = fmaxf(t_lo, 0.f);
+        const float3 ob = make_float3(fmaf(d.x, t_base, o0.x), fmaf(d.y, t_base, o0.y), fmaf(d.z, t_base, o0.z));
+#endif
         if (alive) cn.passes++;
         const Capsule cap = tile_capsule(alive, am, o0, d, t_lo, t_end);
         // ---- phase 1 (cooperative): 32 queued nodes per step against the interval's capsule ----
@@ -738,7 +759,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
                     pos[u] = *src;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) ok[u] = fast_isect(S, pos[u], o0, d, tn[u]);
+                for (int u = 0; u < 4; ++u) ok[u] = fast_isect(S, pos[u], ob, d, t_base, tn[u]);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     bool take = alive && k0 + u < tcn && ok[u] && tn[u] > t_lo && tn[u] <= t_end;
@@ -1218,7 +1239,9 @@ struct TraceArgs {
 };
 
 // ---- forward ----------------------------------------------------------------------------------
-template <int INTEG, int KERNEL, int D, bool TILE>
+// RR: Russian roulette compiled in (a separate instantiation: the 64-bit generator arithmetic in the hit loop costs
+// the roulette-free kernel 9 % through register pressure alone, and no shipped configuration enables it)
+template <int INTEG, int KERNEL, int D, bool TILE, bool RR>
 __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(DevScene S, vp_params P, TraceArgs A)
 {
     extern __shared__ float4 smem_raw[];
@@ -1274,8 +1297,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
         depth += 1;
         cn.hits++;
         if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) return false;  // rf:173-174
-#ifndef VP_NO_RR
-        if (INTEG == VP_INTEGRATOR_RF && P.use_rr) {                          // rf:177-183 (primal pass only)
+        if constexpr (INTEG == VP_INTEGRATOR_RF && RR) {                      // rf:177-183 (primal pass only)
             const float rr_prob = fmaxf(beta, 0.1f);
             if (depth >= P.rr_depth && beta < 0.1f) {
                 beta *= __fdiv_rn(1.f, rr_prob);
@@ -1284,7 +1306,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
                 if (!(u < rr_prob)) return false;
             }
         }
-#endif
         if (!(depth < P.max_depth)) return false;                             // rf:186
         return true;
     };
@@ -1926,9 +1947,15 @@ template <int INTEG, int KERNEL, int D>
 void launch_forward(const DevScene &S, const vp_params &P, const TraceArgs &A, cudaStream_t st)
 {
     int64_t blocks = (A.R + TRACE_THREADS - 1) / TRACE_THREADS;
+    const bool rr = INTEG == VP_INTEGRATOR_RF && P.use_rr;
     // image-shaped launches walk the tree once per 8x4 tile (warp-cooperative); explicit ray batches per ray
-    if (P.image_width > 0) k_trace_forward<INTEG, KERNEL, D, true><<<(unsigned)blocks, TRACE_THREADS, TILE_SMEM, st>>>(S, P, A);
-    else k_trace_forward<INTEG, KERNEL, D, false><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
+    if (P.image_width > 0) {
+        if (rr) k_trace_forward<INTEG, KERNEL, D, true, INTEG == VP_INTEGRATOR_RF><<<(unsigned)blocks, TRACE_THREADS, TILE_SMEM, st>>>(S, P, A);
+        else k_trace_forward<INTEG, KERNEL, D, true, false><<<(unsigned)blocks, TRACE_THREADS, TILE_SMEM, st>>>(S, P, A);
+    } else {
+        if (rr) k_trace_forward<INTEG, KERNEL, D, false, INTEG == VP_INTEGRATOR_RF><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
+        else k_trace_forward<INTEG, KERNEL, D, false, false><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
+    }
 }
 
 template <int INTEG, int KERNEL, int D>
