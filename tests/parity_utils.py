@@ -110,7 +110,13 @@ def compare_forward(res_gpu, res_orc, cap, max_fragile_frac=5e-3, replay=None, s
     bad = robust & ~same
     assert not bad.any(), f"{bad.sum()} robust rays have different hit lists, e.g. ray {np.flatnonzero(bad)[:5]}"
     n_diff = int((~same).sum())
-    assert n_diff <= max_fragile_frac * len(same) + 1, f"{n_diff} of {len(same)} rays differ (all fragile) -- too many"
+    # how many rays may differ: a fixed small fraction, plus -- when the float64 oracle is at hand -- twice the number of
+    # rays on which the fp32 and float64 builds of the oracle THEMSELVES disagree (long lists of sub-millimetre
+    # primitives: at 200 hits per ray every tenth ray contains a hit that rounding decides)
+    budget = max_fragile_frac * len(same) + 1
+    if res_orc64 is not None:
+        budget += 2 * int((~(res_orc.hit_ids[:, :cap] == res_orc64.hit_ids[:, :cap]).all(axis=1)).sum())
+    assert n_diff <= budget, f"{n_diff} of {len(same)} rays differ (all fragile) -- more than the budget of {budget:.0f}"
     ok = np.abs(rgb_g - res_orc.rgb) <= RGB_ATOL + RGB_RTOL * np.abs(res_orc.rgb)
     assert ok[same].all(), f"radiance mismatch: max abs diff {np.abs(rgb_g - res_orc.rgb)[same].max()}"
     if beta_g is not None:
