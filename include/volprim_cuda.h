@@ -87,10 +87,14 @@ typedef struct vp_ray_source {
 } vp_ray_source;
 
 /* Ordered hit lists of a primal pass in compressed-row form (what the adjoint replays instead of walking the BVH a
- * second time).  All arrays are caller-owned DEVICE memory.  Bytes kept per view: 4 per recorded hit + 8 per ray. */
+ * second time).  All arrays are caller-owned DEVICE memory.  Bytes kept per view: 4 (20 with `state`) per recorded
+ * hit + 8 per ray. */
 typedef struct vp_hit_record {
     int64_t *ray_offsets;   /* [n_rays + 1]   list of ray r = ids[ray_offsets[r] .. ray_offsets[r + 1])            */
     int32_t *ids;           /* [capacity]     primitive ids (numbering of vp_set_primitives), front to back        */
+    float *state;           /* [capacity * 4] or NULL: (colour r, g, b, transmittance) of every recorded hit
+                               (volprim_rf).  With it the adjoint's ray-major pass is the PRB recurrence alone --
+                               no primitive is loaded or shaded a second time; 20 instead of 4 bytes per hit          */
     int64_t *total;         /* [2]            entries all lists need; rays whose list was cut at `id_cap`          */
     int64_t capacity;       /* entries `ids` holds (< 2^32).  A record is usable iff total[0] <= capacity and
                                total[1] == 0; vp_render_adjoint does nothing otherwise (the caller re-traces)     */

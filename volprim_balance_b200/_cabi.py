@@ -72,6 +72,7 @@ class vp_hit_record(C.Structure):
     _fields_ = [
         ("ray_offsets", C.c_void_p),
         ("ids", C.c_void_p),
+        ("state", C.c_void_p),
         ("total", C.c_void_p),
         ("capacity", C.c_int64),
         ("id_cap", C.c_int32),

@@ -61,19 +61,23 @@ class RaySource:
 
 
 class HitRecord:
-    """Ordered hit lists of a primal pass in compressed-row form (vp_hit_record): 4 bytes per recorded hit, 8 per ray.  `usable()` reads two device counters (synchronises the stream once)."""
+    """Ordered hit lists of a primal pass in compressed-row form (vp_hit_record): 4 bytes per recorded hit (20 with
+    `with_state`: the primal also leaves every hit's colour and transmittance, and the adjoint's ray-major pass becomes
+    the PRB recurrence alone), 8 per ray.  `usable()` reads two device counters (synchronises the stream once)."""
 
-    def __init__(self, n_rays: int, n_prims: int, capacity: int, id_cap: int, device):
+    def __init__(self, n_rays: int, n_prims: int, capacity: int, id_cap: int, device, with_state: bool = False):
         self.n_rays, self.n_prims = n_rays, n_prims
         self.capacity, self.id_cap = int(max(capacity, 1)), int(id_cap)
         self.ray_offsets = torch.empty(n_rays + 1, dtype=torch.int64, device=device)
         self.ids = torch.empty(self.capacity, dtype=torch.int32, device=device)
+        self.state = torch.empty((self.capacity, 4), dtype=torch.float32, device=device) if with_state else None
         self.total = torch.zeros(2, dtype=torch.int64, device=device)
         self._usable = None
 
     def to_c(self) -> vp_hit_record:
         r = vp_hit_record()
         r.ray_offsets, r.ids = self.ray_offsets.data_ptr(), self.ids.data_ptr()
+        r.state = self.state.data_ptr() if self.state is not None else None
         r.total = self.total.data_ptr()
         r.capacity, r.id_cap = self.capacity, self.id_cap
         return r
@@ -89,7 +93,7 @@ class HitRecord:
         return self._usable
 
     def nbytes(self) -> int:
-        return self.ids.numel() * 4 + self.ray_offsets.numel() * 8
+        return self.ids.numel() * 4 + self.ray_offsets.numel() * 8 + (self.state.numel() * 4 if self.state is not None else 0)
 
     def lists(self):
         """Python view for tests: list of per-ray id arrays (host)."""
@@ -122,6 +126,7 @@ class EllipsoidAccel:
         self.sh_floats = 0
         self.built = False
         self.hits_per_ray_estimate = 48.0   # sizes the next hit record; follows the records actually produced
+        self.state_budget_bytes = 8 << 30   # records above it keep ids only (4 B / hit) and the adjoint re-shades
 
     def close(self):
         if getattr(self, "_h", None):
@@ -222,11 +227,15 @@ class EllipsoidAccel:
     def set_option(self, name: str, value: int):
         _cabi.check(self._lib.vp_set_option(self._h, name.encode(), int(value)), self._h)
 
-    def new_record(self, n_rays: int, id_cap: int, capacity: int | None = None) -> HitRecord:
+    def new_record(self, n_rays: int, id_cap: int, capacity: int | None = None, with_state: bool | None = None) -> HitRecord:
+        """with_state=None: keep the per-hit (colour, transmittance) when the primitives carry colour coefficients and
+        the record stays below `state_budget_bytes` (default 8 GiB)."""
         if capacity is None:
             capacity = int(n_rays * min(float(id_cap), self.hits_per_ray_estimate * 1.3 + 4.0)) + 4096
         capacity = min(capacity, (1 << 32) - 1)
-        return HitRecord(n_rays, self.n, capacity, id_cap, self.device)
+        if with_state is None:
+            with_state = capacity * 16 <= self.state_budget_bytes
+        return HitRecord(n_rays, self.n, capacity, id_cap, self.device, with_state=with_state)
 
     def render_forward(self, params: vp_params, rays: RaySource, record=None, id_cap: int = 0,
                        want_beta: bool = True, want_nhits: bool = True) -> TraceResult:

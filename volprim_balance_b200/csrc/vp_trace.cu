@@ -128,9 +128,21 @@ __device__ __forceinline__ Isect exact_isect(float3 o, float3 d, float4 g0, floa
     return r;
 }
 
+// Work counters.  `hits` is the ray's depth and is taken from there at the end; `overflow` (traversal-stack overflow:
+// must stay 0) and `retries` are touched on rare paths only.  The three per-step work counters (candidates, nodes,
+// passes) are compiled in with -DVP_FULL_STATS (profiling builds): three registers kept alive through the whole walk
+// are not free in a kernel that runs at its register cap.
 struct Counters {
-    uint32_t hits, candidates, nodes, passes, overflow, retries;
+    uint32_t hits, overflow, retries;
+#ifdef VP_FULL_STATS
+    uint32_t candidates, nodes, passes;
+#endif
 };
+#ifdef VP_FULL_STATS
+#define VP_COUNT(x) x
+#else
+#define VP_COUNT(x) do { } while (0)
+#endif
 
 // Approximate entry distance from the pre-transformed record xf (rows of M = diag(1/(extent s)) R^T with the
 // centre in .w).  Only used to ORDER candidates and to bin them into intervals; validity is conservative
@@ -307,7 +319,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
         bool overflow = false;
         float best_t = VP_INF;
         int best_pos = -1;
-        if (alive) cn.passes++;
+        VP_COUNT(if (alive) cn.passes++);
         // ---- phase 1: collect the leaves whose boxes meet [t_lo, t_end] ----
         // The loop body is branch-free per lane (predicated appends / push / pop): lanes differ only in their
         // trip count.  Leaves are appended from their parent and never become the current node.
@@ -319,7 +331,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
             const float4 *nd = S.nodes + 4ll * node;
             float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
             const int top = stack[sp > 0 ? sp - 1 : 0];                   // speculative: used only on a pop
-            cn.nodes++;
+            VP_COUNT(cn.nodes++);
             const bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), oi, inv, t_lo, t_end);
             const bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), oi, inv, t_lo, t_end);
             const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
@@ -355,7 +367,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
             while (cnode != NODE_SENTINEL) {
                 if (cnode < 0) {
                     float tn;
-                    cn.candidates++;
+                    VP_COUNT(cn.candidates++);
                     if (fast_isect(S, ~cnode, ob, d, t_base, tn) && tn > t_lo && tn < best_t) {
                         best_t = tn;
                         best_pos = ~cnode;
@@ -366,7 +378,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
                 }
                 const float4 *nd = S.nodes + 4ll * cnode;
                 float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
-                cn.nodes++;
+                VP_COUNT(cn.nodes++);
                 const bool hl = slab(make_float3(n0.x, n0.y, n0.z), make_float3(n0.w, n1.x, n1.y), oi, inv, t_lo, t_end);
                 const bool hr = slab(make_float3(n1.z, n1.w, n2.x), make_float3(n2.y, n2.z, n2.w), oi, inv, t_lo, t_end);
                 const int left = __float_as_int(n3.x), right = __float_as_int(n3.y);
@@ -396,7 +408,7 @@ __device__ __forceinline__ void walk_ray(const DevScene &S, int *s_id, float *s_
                     n_new += tn > t_start ? 1 : 0;
                 }
             }
-            cn.candidates += n_c;
+            VP_COUNT(cn.candidates += n_c);
         }
         __syncwarp();
         // ---- phase 3: drain in increasing distance ----
@@ -678,7 +690,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         const float t_base = fmaxf(t_lo, 0.f);
         const float3 ob = make_float3(fmaf(d.x, t_base, o0.x), fmaf(d.y, t_base, o0.y), fmaf(d.z, t_base, o0.z));
 #endif
-        if (alive) cn.passes++;
+        VP_COUNT(if (alive) cn.passes++);
         const Capsule cap = tile_capsule(alive, am, o0, d, t_lo, t_end);
         // ---- phase 1 (cooperative): 32 queued nodes per step against the interval's capsule ----
         int qn = rs_n, tcn = 0;
@@ -696,7 +708,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
             if (node >= 0) {
                 bool hl, hr;
                 capsule_children(S, node, cap, hl, hr, left, right);
-                cn.nodes++;
+                VP_COUNT(cn.nodes++);
                 iL = hl && left >= 0; lL = hl && left < 0;
                 iR = hr && right >= 0; lR = hr && right < 0;
             }
@@ -776,7 +788,7 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
                     }
                 }
             }
-            if (alive) cn.candidates += tcn;
+            VP_COUNT(if (alive) cn.candidates += tcn);
         }
         if (overflow) {   // the tile's candidate list or the node queue did not fit: shorter interval, walk again
             if (alive) cn.retries++;   // (statistics)
@@ -1133,15 +1145,21 @@ __device__ __forceinline__ int64_t ray_index(int64_t t, int W, int H)
 __device__ __forceinline__ void flush_counters(const Counters &cn, vp_stats *st)
 {
     if (!st) return;
+#ifdef VP_FULL_STATS
     uint32_t v[6] = { cn.hits, cn.candidates, cn.nodes, cn.passes, cn.overflow, cn.retries };
+#else
+    uint32_t v[6] = { cn.hits, 0u, 0u, 0u, cn.overflow, cn.retries };
+#endif
 #pragma unroll
     for (int k = 0; k < 6; ++k)
         for (int off = 16; off; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
     if ((threadIdx.x & 31) == 0) {
         atomicAdd((unsigned long long *)&st->hits, (unsigned long long)v[0]);
+#ifdef VP_FULL_STATS
         atomicAdd((unsigned long long *)&st->candidates, (unsigned long long)v[1]);
         atomicAdd((unsigned long long *)&st->node_visits, (unsigned long long)v[2]);
         atomicAdd((unsigned long long *)&st->passes, (unsigned long long)v[3]);
+#endif
         if (v[4]) atomicAdd((unsigned long long *)&st->stack_overflows, (unsigned long long)v[4]);
         if (v[5]) atomicAdd((unsigned long long *)&st->interval_retries, (unsigned long long)v[5]);
     }
@@ -1226,6 +1244,7 @@ struct TraceArgs {
     float *rgb, *T;
     uint32_t *nhits;
     int32_t *ids;            // forward: hit-id output (dense, strides rs / hs)
+    float4 *hit_state;       // forward, optional (volprim_rf): (colour rgb, transmittance) of every recorded hit, same indexing
     int32_t cap;
     int64_t rs, hs;
     // adjoint
@@ -1233,6 +1252,7 @@ struct TraceArgs {
     const int32_t *rec_ids;       // replay: dense (rs, hs, rec_counts, cap) or compressed rows (rec_offsets, stride 1)
     const uint32_t *rec_counts;
     const int64_t *rec_offsets;
+    const float4 *rec_state; // replay of a record that carries the per-hit (colour, transmittance)
     float *g_data, *g_attr, *g_sh;
     GatherBuf gb;
     vp_stats *stats;
@@ -1241,14 +1261,16 @@ struct TraceArgs {
 // ---- forward ----------------------------------------------------------------------------------
 // RR: Russian roulette compiled in (a separate instantiation: the 64-bit generator arithmetic in the hit loop costs
 // the roulette-free kernel 9 % through register pressure alone, and no shipped configuration enables it)
-template <int INTEG, int KERNEL, int D, bool TILE, bool RR>
+// REC: hit lists (and, for volprim_rf, the per-hit colour + transmittance) are written out; the plain instantiation
+// carries no store in its hit loop at all.
+template <int INTEG, int KERNEL, int D, bool TILE, bool RR, bool REC>
 __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(DevScene S, vp_params P, TraceArgs A)
 {
     extern __shared__ float4 smem_raw[];
     int *s_id = reinterpret_cast<int *>(smem_raw) + threadIdx.x;
     float *s_t = reinterpret_cast<float *>(smem_raw) + CAND_CAP * TRACE_THREADS + threadIdx.x;
     const int64_t t = (int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x;
-    Counters cn = { 0, 0, 0, 0, 0, 0 };
+    Counters cn = {};
     const bool in_range = t < A.R;
     const int64_t r = in_range ? ray_index(t, P.image_width, P.image_height) : 0;
     float3 o = make_float3(0.f, 0.f, 0.f), d = make_float3(0.f, 0.f, 1.f);
@@ -1273,12 +1295,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
                 sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw);
             }
             const float omt = 1.f - T;
+            float col[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                float col = (D >= 0) ? fmaxf(raw[ch], 0.f) : 0.f;
-                float le = beta * omt * col;           // rf:140
+                col[ch] = (D >= 0) ? fmaxf(raw[ch], 0.f) : 0.f;
+                float le = beta * omt * col[ch];       // rf:140
                 if (!isfinite(le)) le = 0.f;            // rf:141
                 L[ch] += le;                            // rf:145
+            }
+            if constexpr (REC) {
+                // what the adjoint's ray pass needs of this hit: with (colour, T) on record it is a pure recurrence
+                if (A.hit_state && depth < (uint32_t)A.cap)
+                    A.hit_state[r * A.rs + depth * A.hs] = make_float4(col[0], col[1], col[2], T);
             }
         } else {
             float rho = (KERNEL == VP_KERNEL_GAUSSIAN) ? gauss_density_integral(g1, is)
@@ -1289,13 +1317,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
         // (no atomics in this kernel: a RED anywhere in the hit loop -- even one that never executes -- stops ptxas from
         // moving the loads of the drain across it and doubled the kernel's time; per-primitive hit counts are taken from
         // the compressed record in a flat pass of the adjoint instead)
-        if (A.ids && depth < (uint32_t)A.cap) A.ids[r * A.rs + depth * A.hs] = __float_as_int(g1.w);
+        if constexpr (REC) {
+            if (depth < (uint32_t)A.cap) A.ids[r * A.rs + depth * A.hs] = __float_as_int(g1.w);
+        }
         // ray.o = si.p + ray.d * 1e-4                     rf:149 / tomo:114
         o.x = fmaf(d.x, P.eps_advance, fmaf(d.x, is.tn, o.x));
         o.y = fmaf(d.y, P.eps_advance, fmaf(d.y, is.tn, o.y));
         o.z = fmaf(d.z, P.eps_advance, fmaf(d.z, is.tn, o.z));
         depth += 1;
-        cn.hits++;
         if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) return false;  // rf:173-174
         if constexpr (INTEG == VP_INTEGRATOR_RF && RR) {                      // rf:177-183 (primal pass only)
             const float rr_prob = fmaxf(beta, 0.1f);
@@ -1329,6 +1358,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
         // (hit lists are not padded: a ray's entries beyond its count are never read -- 75 % of the dense block on
         // the headline configuration used to be -1 fill)
     }
+    cn.hits = depth;
     flush_counters(cn, A.stats);
 }
 
@@ -1573,7 +1603,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE != ADJ_WALK ? VP_REPLAY_BL
     int *s_id = reinterpret_cast<int *>(smem_raw) + threadIdx.x;
     float *s_t = reinterpret_cast<float *>(smem_raw) + CAND_CAP * TRACE_THREADS + threadIdx.x;
     const int64_t t = (int64_t)blockIdx.x * TRACE_THREADS + threadIdx.x;
-    Counters cn = { 0, 0, 0, 0, 0, 0 };
+    Counters cn = {};
     if constexpr (MODE == ADJ_REPLAY_ROWS || MODE == ADJ_REPLAY_BUCKET)
         if (!record_usable(A.gb)) return;            // truncated record: the caller re-traces (see vp_hit_record)
     const bool in_range = t < A.R;
@@ -1616,7 +1646,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE != ADJ_WALK ? VP_REPLAY_BL
             o.z = fmaf(d.z, P.eps_advance, fmaf(d.z, is.tn, o.z));
         }
         depth += 1;
-        cn.hits++;
         if (INTEG == VP_INTEGRATOR_RF && !(beta > P.t_cutoff)) return false;
         if (!(depth < P.max_depth)) return false;
         return true;
@@ -1671,6 +1700,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE != ADJ_WALK ? VP_REPLAY_BL
         if constexpr (TILE) walk_tile(S, reinterpret_cast<int *>(smem_raw), o, o0, d, maxt, alive, missed, cn, interact);
         else walk_ray(S, s_id, s_t, o, o0, d, maxt, alive, missed, cn, interact);
     }
+    cn.hits = depth;
     flush_counters(cn, A.stats);
 }
 
@@ -1931,6 +1961,80 @@ __global__ void __launch_bounds__(128) k_compact_hits(const int32_t *__restrict_
     }
 }
 
+// the same for the per-hit (colour, transmittance) records: 16-byte elements, two warps per block
+__global__ void __launch_bounds__(64) k_compact_state(const float4 *__restrict__ dense, int64_t n, const uint32_t *__restrict__ counts,
+                                                      const int64_t *__restrict__ offsets, float4 *__restrict__ out, int64_t capacity)
+{
+    __shared__ float4 tile[2][32][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t r0 = ((int64_t)blockIdx.x * 2 + wid) * 32;
+    if (r0 >= n) return;
+    const int64_t r = r0 + lane;
+    const uint32_t c = r < n ? counts[r] : 0u;
+    const int64_t off = r < n ? offsets[r] : 0;
+    const uint32_t cmax = __reduce_max_sync(0xffffffffu, c);
+    for (uint32_t k0 = 0; k0 < cmax; k0 += 32) {
+        const uint32_t kn = min(32u, cmax - k0);
+        for (uint32_t k = 0; k < kn; ++k)
+            if (k0 + k < c) tile[wid][k][lane] = dense[(int64_t)(k0 + k) * n + r];
+        __syncwarp();
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t cj = __shfl_sync(0xffffffffu, c, j);
+            const int64_t oj = __shfl_sync(0xffffffffu, off, j);
+            if (k0 + lane < cj && oj + cj <= capacity) out[oj + k0 + lane] = tile[wid][lane][j];
+        }
+        __syncwarp();
+    }
+}
+
+// Ray-major pass of the gather adjoint when the record carries the per-hit (colour, transmittance): the PRB recurrences
+// of volprim_rf.py:137-165 alone -- no primitive is loaded, nothing is intersected or shaded again.  One thread per ray
+// walks its row of the record and leaves (d colour, d alpha) in the bucket slot of every hit.
+__global__ void __launch_bounds__(256) k_adjoint_rows(int64_t R, const float *__restrict__ dL, const float *__restrict__ state_in,
+                                                      const int64_t *__restrict__ offsets, const int32_t *__restrict__ ids,
+                                                      const float4 *__restrict__ hit_state, GatherBuf gb, vp_params P)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R || !record_usable(gb)) return;
+    const float g[3] = { dL[3 * r], dL[3 * r + 1], dL[3 * r + 2] };
+    if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) return;                        // rf:111-112
+    float L[3] = { state_in[3 * r], state_in[3 * r + 1], state_in[3 * r + 2] };
+    float beta = 1.f;
+    const int64_t e0 = offsets[r], e1 = offsets[r + 1];
+    const float t_clamped = 1.f - 0.9999f;        // T of a hit whose alpha was clamped (rf:76): no gradient to opacity / geometry
+    float4 st_next = e0 < e1 ? __ldcs(hit_state + e0) : make_float4(0.f, 0.f, 0.f, 1.f);
+    for (int64_t e = e0; e < e1; ++e) {
+        const float4 st = st_next;
+        if (e + 1 < e1) st_next = __ldcs(hit_state + e + 1);
+        const float T = st.w, omt = 1.f - T;
+        const float col[3] = { st.x, st.y, st.z };
+        float dalpha = 0.f, dcol[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float le = beta * omt * col[ch];
+            const bool lef = isfinite(le);
+            if (!lef) le = 0.f;
+            L[ch] -= le;                                  // rf:145 (adjoint branch)
+            const float lo = le + L[ch] * T / T;          // rf:156-159
+            dcol[ch] = 0.f;
+            if (isfinite(lo)) {                           // rf:160
+                if (lef) {
+                    dalpha += g[ch] * beta * col[ch];
+                    if (col[ch] > 0.f) dcol[ch] = g[ch] * beta * omt;
+                }
+                dalpha -= g[ch] * L[ch] / T;
+            }
+        }
+        if (!(T > t_clamped)) dalpha = 0.f;
+        if (dalpha != 0.f || dcol[0] != 0.f || dcol[1] != 0.f || dcol[2] != 0.f) {
+            const uint32_t slot = __ldg(gb.offsets + __ldcs(ids + e)) + __ldcs(gb.rank + e);
+            gb.state[slot] = make_float4(dcol[0], dcol[1], dcol[2], dalpha);
+            gb.ray[slot] = (uint32_t)r;
+        }
+        beta *= T;
+    }
+}
+
 __global__ void k_raygen(RaySrc S, int64_t total, float *__restrict__ ro, float *__restrict__ rd, float *__restrict__ rmaxt)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1946,16 +2050,24 @@ __global__ void k_raygen(RaySrc S, int64_t total, float *__restrict__ ro, float 
 template <int INTEG, int KERNEL, int D>
 void launch_forward(const DevScene &S, const vp_params &P, const TraceArgs &A, cudaStream_t st)
 {
-    int64_t blocks = (A.R + TRACE_THREADS - 1) / TRACE_THREADS;
-    const bool rr = INTEG == VP_INTEGRATOR_RF && P.use_rr;
-    // image-shaped launches walk the tree once per 8x4 tile (warp-cooperative); explicit ray batches per ray
+    const unsigned blocks = (unsigned)((A.R + TRACE_THREADS - 1) / TRACE_THREADS);
+    constexpr bool RF = INTEG == VP_INTEGRATOR_RF;
+    const bool rr = RF && P.use_rr, rec = A.ids != nullptr;
+    // image-shaped launches walk the tree once per 8x4 tile (warp-cooperative); explicit ray batches per ray.
+    // Instantiations: plain, recording, Russian roulette (+ recording only for the dense debug lists of explicit batches).
+#define VP_FWD(TILE, RR, REC, SMEM) k_trace_forward<INTEG, KERNEL, D, TILE, RR, REC><<<blocks, TRACE_THREADS, SMEM, st>>>(S, P, A)
     if (P.image_width > 0) {
-        if (rr) k_trace_forward<INTEG, KERNEL, D, true, INTEG == VP_INTEGRATOR_RF><<<(unsigned)blocks, TRACE_THREADS, TILE_SMEM, st>>>(S, P, A);
-        else k_trace_forward<INTEG, KERNEL, D, true, false><<<(unsigned)blocks, TRACE_THREADS, TILE_SMEM, st>>>(S, P, A);
+        if (rr && rec) VP_FWD(true, RF, true, TILE_SMEM);
+        else if (rr) VP_FWD(true, RF, false, TILE_SMEM);
+        else if (rec) VP_FWD(true, false, true, TILE_SMEM);
+        else VP_FWD(true, false, false, TILE_SMEM);
     } else {
-        if (rr) k_trace_forward<INTEG, KERNEL, D, false, INTEG == VP_INTEGRATOR_RF><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
-        else k_trace_forward<INTEG, KERNEL, D, false, false><<<(unsigned)blocks, TRACE_THREADS, TRACE_SMEM, st>>>(S, P, A);
+        if (rr && rec) VP_FWD(false, RF, true, TRACE_SMEM);
+        else if (rr) VP_FWD(false, RF, false, TRACE_SMEM);
+        else if (rec) VP_FWD(false, false, true, TRACE_SMEM);
+        else VP_FWD(false, false, false, TRACE_SMEM);
     }
+#undef VP_FWD
 }
 
 template <int INTEG, int KERNEL, int D>
@@ -2092,6 +2204,7 @@ int check_record(vp_ctx *ctx, const vp_hit_record *rec, const char *who)
         return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record arrays (ray_offsets, ids, total) are required");
     if (rec->capacity <= 0 || rec->capacity >= (1ll << 32) || rec->id_cap <= 0)
         return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record needs 0 < capacity < 2^32 and id_cap > 0");
+    if (rec->state && (uintptr_t)rec->state % 16) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record state must be 16-byte aligned");
     return VP_OK;
 }
 
@@ -2200,8 +2313,9 @@ int vp_render_forward_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sour
         return VP_OK;
     }
     const int cap = rec->id_cap;
+    const bool with_state = rec->state != nullptr && P.integrator == VP_INTEGRATOR_RF;
     int64_t band;                                     // rays per band
-    const int64_t fit = ctx->record_scratch_bytes / ((int64_t)cap * 4);
+    const int64_t fit = ctx->record_scratch_bytes / ((int64_t)cap * (with_state ? 20 : 4));
     const int64_t per_image = P.image_width > 0 ? (int64_t)P.image_width * P.image_height : 0;
     int64_t rows_per_band = 0;
     if (per_image > 0) {
@@ -2215,6 +2329,7 @@ int vp_render_forward_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sour
         if (band > R) band = R;
     }
     if ((rc = vp_ensure(ctx, ctx->rec_dense, sizeof(int32_t) * (size_t)cap * (size_t)band))) return rc;
+    if (with_state && (rc = vp_ensure(ctx, ctx->rec_dense_state, sizeof(float4) * (size_t)cap * (size_t)band))) return rc;
     if ((rc = vp_ensure(ctx, ctx->rec_counts, sizeof(uint32_t) * (size_t)band))) return rc;
     if ((rc = vp_ensure(ctx, ctx->scan_tmp, sizeof(uint64_t) * (size_t)(vpscan::n_tiles(band) + 1)))) return rc;
     uint32_t *nh_all = nhits;
@@ -2240,6 +2355,7 @@ int vp_render_forward_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sour
         B.T = T ? T + first : nullptr;
         B.nhits = nh_all + first;
         B.ids = (int32_t *)ctx->rec_dense.ptr; B.cap = cap; B.rs = 1; B.hs = cnt;
+        B.hit_state = with_state ? (float4 *)ctx->rec_dense_state.ptr : nullptr;
         if ((rc = dispatch<0>(ctx, S, Pb, B, nullptr, st))) return rc;
         const unsigned blocks = (unsigned)((cnt + 255) / 256), cblocks = (unsigned)((cnt + 127) / 128);
         k_record_counts<<<blocks, 256, 0, st>>>(B.nhits, cnt, cap, (uint32_t *)ctx->rec_counts.ptr, rec->total);
@@ -2249,6 +2365,10 @@ int vp_render_forward_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sour
                                                    (unsigned long long *)rec->ray_offsets + first + cnt, st);
         k_compact_hits<<<cblocks, 128, 0, st>>>((const int32_t *)ctx->rec_dense.ptr, cnt, (const uint32_t *)ctx->rec_counts.ptr,
                                                rec->ray_offsets + first, rec->ids, rec->capacity);
+        if (with_state)
+            k_compact_state<<<(unsigned)((cnt + 63) / 64), 64, 0, st>>>((const float4 *)ctx->rec_dense_state.ptr, cnt,
+                                                                         (const uint32_t *)ctx->rec_counts.ptr, rec->ray_offsets + first,
+                                                                         (float4 *)rec->state, rec->capacity);
         first += cnt;
     }
     VP_CUDA_CHECK(ctx, cudaGetLastError());
@@ -2335,6 +2455,12 @@ int vp_adjoint_begin_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sourc
     }
     A.gb = gather_buf(ctx, rec);
     if (R == 0) return VP_OK;
+    if (P.integrator == VP_INTEGRATOR_RF && rec->state) {
+        k_adjoint_rows<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, dL, state_in, rec->ray_offsets, rec->ids,
+                                                                   (const float4 *)rec->state, A.gb, P);
+        VP_CUDA_CHECK(ctx, cudaGetLastError());
+        return VP_OK;
+    }
     if ((rc = dispatch<1>(ctx, S, P, A, nullptr, st))) return rc;
     VP_CUDA_CHECK(ctx, cudaGetLastError());
     return VP_OK;

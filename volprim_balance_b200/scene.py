@@ -406,7 +406,8 @@ def _render_primal_impl(scene, sensor, integrator, seed, spp, jitter, record, ro
         rays = RaySource(camera=s.vp_camera(), spp=spp, jitter=jit, rows=band)
         want = bool(record)
         if want:   # budget over the views of this call
-            need = int(rays.n_rays * (acc.hits_per_ray_estimate * 1.3 + 4.0) * 4) + rays.n_rays * 8
+            entries = int(rays.n_rays * (acc.hits_per_ray_estimate * 1.3 + 4.0))
+            need = entries * (20 if entries * 16 <= acc.state_budget_bytes else 4) + rays.n_rays * 8
             want = need <= budget
             budget -= need if want else 0
         res = acc.render_forward(params, rays, record=want, id_cap=integrator._cap(), want_beta=False, want_nhits=False)
