@@ -88,18 +88,24 @@ typedef struct vp_ray_source {
 
 /* Ordered hit lists of a primal pass in compressed-row form (what the adjoint replays instead of walking the BVH a
  * second time).  All arrays are caller-owned DEVICE memory.  Bytes kept per view: 4 (20 with `state`) per recorded
- * hit + 8 per ray. */
+ * hit + 8 per ray; or a dense block (see `dense`). */
 typedef struct vp_hit_record {
-    int64_t *ray_offsets;   /* [n_rays + 1]   list of ray r = ids[ray_offsets[r] .. ray_offsets[r + 1])            */
-    int32_t *ids;           /* [capacity]     primitive ids (numbering of vp_set_primitives), front to back        */
-    float *state;           /* [capacity * 4] or NULL: (colour r, g, b, transmittance) of every recorded hit
-                               (volprim_rf).  With it the adjoint's ray-major pass is the PRB recurrence alone --
-                               no primitive is loaded or shaded a second time; 20 instead of 4 bytes per hit          */
-    int64_t *total;         /* [2]            entries all lists need; rays whose list was cut at `id_cap`          */
-    int64_t capacity;       /* entries `ids` holds (< 2^32).  A record is usable iff total[0] <= capacity and
-                               total[1] == 0; vp_render_adjoint does nothing otherwise (the caller re-traces)     */
-    int32_t id_cap;         /* most hits recorded per ray (height of the transient dense scratch)                  */
-    int32_t reserved;
+    int64_t *ray_offsets;   /* rows:  [n_rays + 1]   list of ray r = ids[ray_offsets[r] .. ray_offsets[r + 1])      */
+    int32_t *ids;           /* rows:  [capacity] primitive ids (numbering of vp_set_primitives), front to back
+                               dense: [id_cap * n_rays], hit k of ray r at ids[k * n_rays + r]                      */
+    float *state;           /* rows:  [capacity * 4] or NULL; dense: [id_cap * n_rays * 4], same indexing:
+                               (colour r, g, b, transmittance) of every recorded hit (volprim_rf).  With it the
+                               adjoint's ray-major pass is the PRB recurrence alone -- no primitive is loaded or
+                               shaded a second time; 20 instead of 4 bytes per hit                                  */
+    uint32_t *counts;       /* dense: [n_rays] recorded hits per ray (written by vp_render_forward); rows: unused   */
+    int64_t *total;         /* [2]            entries all lists hold; rays whose list was cut at `id_cap`          */
+    int64_t capacity;       /* rows: entries `ids` holds; dense: the bound on the entries the gather adjoint sizes its
+                               buckets with (< 2^32).  A record is usable iff total[0] <= capacity and total[1] == 0;
+                               vp_render_adjoint does nothing otherwise (the caller re-traces)                     */
+    int32_t id_cap;         /* most hits recorded per ray                                                          */
+    int32_t dense;          /* 0: compressed rows (4 or 20 bytes per hit, compacted from a transient band scratch);
+                               1: dense hit-major block in the caller's buffers with per-hit state -- no compaction
+                               pass, coalesced replay: 20 B * id_cap * n_rays of memory for the fastest step        */
 } vp_hit_record;
 
 /* Reconstruction filters of the film (Mitsuba rfilter plugins `box`, `tent`, `gaussian`; volprim/cameras.py:117). */
@@ -182,7 +188,7 @@ VP_API int vp_render_forward(vp_ctx *ctx, const vp_params *params, const vp_ray_
 
 /* vp_render_adjoint: Integrator.sample(Backward) replaying `record` (volprim_rf.py:106-165).  volprim_rf uses the
  * GATHER formulation: a flat counting pass over the record sizes one bucket per primitive, a ray-major pass replays
- * every list and writes 20 B of per-hit state into the bucket of the hit primitive, then one warp per primitive (and
+ * every list and writes a 32-byte entry per hit (one full-sector store) into the bucket of the hit primitive, then one warp per primitive (and
  * per further 256 entries of a big bucket) accumulates its bucket in registers and adds the 10 + 1 + C gradient floats
  * to the caller's buffers -- no per-hit global reductions (the scatter formulation of vp_trace_adjoint saturates the L2
  * reduction units).  volprim_tomography replays with vector reductions like vp_trace_adjoint.
@@ -215,7 +221,8 @@ VP_API int vp_film_adjoint(int32_t width, int32_t height, int32_t spp, int32_t r
                            void *stream);
 
 /* Tunables of a context: "record_scratch_bytes" (transient dense hit-list scratch of vp_render_forward, default
- * 1 GiB).  Returns VP_E_INVALID for an unknown name. */
+ * 6 GiB: a 1080p view with per-hit state at a cap of 128 hits fits one band; every band is a kernel launch with its own
+ * tail).  Returns VP_E_INVALID for an unknown name. */
 VP_API int vp_set_option(vp_ctx *ctx, const char *name, int64_t value);
 
 /* Copy the work counters of the most recent trace call to the host (synchronises `stream`). */

@@ -71,6 +71,14 @@ def main():
             acc.hits_per_ray_estimate = hits / V / R * 1.08
             id_cap = 128 if wl.get("max_depth", 128) > 0 else 1024
             fa = bench.time_fwd_adjoint(torch, acc, params, sens, list(range(V)), id_cap, R, cloud.n, 48, reps=V)
+            if "--buckets" in sys.argv:
+                rec = acc.new_record(R, id_cap, with_state=False)
+                acc.render_forward(params, RaySource(camera=sens[0].vp_camera()), record=rec, id_cap=id_cap)
+                tot = rec.totals()[0]
+                cnt = torch.bincount(rec.ids[:tot].long(), minlength=cloud.n)
+                edges = [0, 1, 9, 33, 65, 257, 1025, 1 << 30]
+                out["buckets"] = {f"{a}..{b - 1}": [round(float(((cnt >= a) & (cnt < b)).float().mean()), 4),
+                                                     round(float(cnt[(cnt >= a) & (cnt < b)].sum()) / tot, 4)] for a, b in zip(edges, edges[1:])}
             out.update({k: round(v, 4) if isinstance(v, float) else v for k, v in fa.items()})
         print(json.dumps(out), flush=True)
         del scene, shape, acc, cloud

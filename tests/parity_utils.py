@@ -233,10 +233,17 @@ def check_gradients(got, want, noise, what, split_data=True):
 
 def record_lists(rec, rays, cap):
     """Dense [len(rays), cap] -1 padded id lists + counts of the selected rays of a compressed-row hit record."""
-    off = rec.ray_offsets.cpu().numpy()
-    ids = rec.ids.cpu().numpy()
     out = np.full((len(rays), cap), -1, np.int32)
     cnt = np.zeros(len(rays), np.int64)
+    if rec.dense:
+        sel = torch.as_tensor(np.asarray(list(rays), np.int64), device=rec.ids.device)
+        ids = rec.ids[:, sel].t().cpu().numpy()
+        cnt = rec.counts[sel].cpu().numpy().astype(np.int64)
+        n = min(cap, ids.shape[1])
+        out[:, :n] = np.where(np.arange(n)[None, :] < cnt[:, None], ids[:, :n], -1)
+        return out, cnt
+    off = rec.ray_offsets.cpu().numpy()
+    ids = rec.ids.cpu().numpy()
     for k, r in enumerate(rays):
         a, b = off[r], off[r + 1]
         n = min(b - a, cap)

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     # struct layouts must match the header (sizes are part of the ABI)
     assert ctypes.sizeof(_cabi.vp_params) == 64 and ctypes.sizeof(_cabi.vp_camera) == 76
     assert ctypes.sizeof(_cabi.vp_stats) == 56 and ctypes.sizeof(_cabi.vp_ray_source) == 56
-    assert ctypes.sizeof(_cabi.vp_hit_record) == 48
+    assert ctypes.sizeof(_cabi.vp_hit_record) == 56
     # the structs of the header and of the ctypes mirror list the same fields in the same order
     for name, cls in (("vp_params", _cabi.vp_params), ("vp_camera", _cabi.vp_camera), ("vp_ray_source", _cabi.vp_ray_source),
                       ("vp_hit_record", _cabi.vp_hit_record), ("vp_stats", _cabi.vp_stats)):

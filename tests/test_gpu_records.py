@@ -64,7 +64,7 @@ def test_compressed_hit_records_equal_the_dense_lists(scratch):
     o, d, mt = acc.raygen_perspective(s.vp_camera(), 1, None)
     dense = acc.trace_forward(p, o, d, mt, record_cap=64)
     p0, _ = make_params(0, 0, 64)
-    res = acc.render_forward(p0, RaySource(camera=s.vp_camera()), record=acc.new_record(128 * 64, 64, with_state=False), id_cap=64)
+    res = acc.render_forward(p0, RaySource(camera=s.vp_camera()), record=acc.new_record(128 * 64, 64, with_state=False, dense=False), id_cap=64)
     rec = res.record
     assert rec.usable() and torch.equal(res.rgb, dense.rgb) and torch.equal(res.nhits, dense.nhits)
     nh = dense.nhits.cpu().numpy().astype(np.int64)
@@ -77,7 +77,7 @@ def test_compressed_hit_records_equal_the_dense_lists(scratch):
     assert rec.ids.numel() >= off[-1] and rec.nbytes() == rec.ids.numel() * 4 + (128 * 64 + 1) * 8
     # the state record: (colour, transmittance) per hit -- the product of (1 - T) along a row is the ray's final beta,
     # and compositing the recorded colours reproduces the image (sRGB -> linear at the end)
-    rich = acc.render_forward(p0, RaySource(camera=s.vp_camera()), record=acc.new_record(128 * 64, 64, with_state=True), id_cap=64)
+    rich = acc.render_forward(p0, RaySource(camera=s.vp_camera()), record=acc.new_record(128 * 64, 64, with_state=True, dense=False), id_cap=64)
     assert rich.record.usable() and torch.equal(rich.record.ids[:off[-1]], rec.ids[:off[-1]]) and torch.equal(rich.rgb, res.rgb)
     st = rich.record.state[:off[-1]].cpu().numpy().astype(np.float64)
     row = np.repeat(np.arange(128 * 64), nh)
@@ -90,18 +90,25 @@ def test_compressed_hit_records_equal_the_dense_lists(scratch):
     np.add.at(Ls, row[rows97], (beta_before * (1 - st[rows97, 3]))[:, None] * st[rows97, :3])
     lin = np.where(Ls <= 0.04045, Ls / 12.92, ((np.maximum(Ls, 0.04045) + 0.055) / 1.055) ** 2.4)[::97]
     np.testing.assert_allclose(lin, res.rgb.cpu().numpy()[::97], rtol=1e-4, atol=1e-6)
+    # the dense record: the same lists and states hit-major in the record's own buffers, no compaction pass
+    dn = acc.render_forward(p0, RaySource(camera=s.vp_camera()), record=acc.new_record(128 * 64, 64, dense=True), id_cap=64)
+    assert dn.record.dense and dn.record.usable() and dn.record.totals() == (int(nh.sum()), 0)
+    assert torch.equal(dn.record.counts, dense.nhits) and torch.equal(dn.rgb, res.rgb)
+    valid = torch.arange(64, device="cuda")[:, None] < dn.record.counts[None, :]
+    assert torch.equal(dn.record.ids[valid], dense.hit_ids[valid])
+    assert torch.equal(dn.record.state.permute(1, 0, 2)[valid.t()], rich.record.state[:off[-1]])
     # a record that is too small is reported, not silently truncated
-    small = acc.new_record(128 * 64, 64, capacity=1000)
+    small = acc.new_record(128 * 64, 64, capacity=1000, dense=False)
     acc.render_forward(p0, RaySource(camera=s.vp_camera()), record=small, id_cap=64)
     assert not small.usable() and small.totals()[0] == int(nh.sum())
-    cut = acc.new_record(128 * 64, 8)
+    cut = acc.new_record(128 * 64, 8, dense=False)
     acc.render_forward(p0, RaySource(camera=s.vp_camera()), record=cut, id_cap=8)
     assert not cut.usable() and cut.totals()[1] == int((nh > 8).sum())
 
 
-@pytest.mark.parametrize("with_state", [True, False], ids=["state_record", "id_record"])
+@pytest.mark.parametrize("kind", ["dense", "rows_state", "rows"])
 @pytest.mark.parametrize("kernel,deg", [(0, 3), (1, 3), (0, 1), (1, 0), (0, 2)])
-def test_gather_adjoint_matches_oracle_and_scatter_adjoint(kernel, deg, with_state):
+def test_gather_adjoint_matches_oracle_and_scatter_adjoint(kernel, deg, kind):
     """volprim_rf adjoint through vp_render_adjoint (ray-major pass into per-primitive buckets + one warp per
     primitive, no global reductions) against the oracle, elementwise at 1e-3, and against the scatter formulation."""
     cloud = _cloud(n=6000, crossings=35, deg=deg)
@@ -111,8 +118,8 @@ def test_gather_adjoint_matches_oracle_and_scatter_adjoint(kernel, deg, with_sta
     o, d, mt = _gpu_rays(acc, s)
     p, op = make_params(0, kernel, 128)
     rays = RaySource(camera=s.vp_camera())
-    fwd = acc.render_forward(p, rays, record=acc.new_record(o.shape[0], 128, with_state=with_state), id_cap=128)
-    assert (fwd.record.state is not None) == with_state
+    fwd = acc.render_forward(p, rays, record=acc.new_record(o.shape[0], 128, with_state=kind != "rows", dense=kind == "dense"), id_cap=128)
+    assert (fwd.record.state is not None) == (kind != "rows") and fwd.record.dense == (kind == "dense") and fwd.record.usable()
     osc = oracle_scene(cloud)
     ref = osc.forward(op, o, d, mt, cap=128, fragility=True)
     ids_g, _ = record_lists(fwd.record, range(o.shape[0]), 128)

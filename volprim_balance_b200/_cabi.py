@@ -73,10 +73,11 @@ class vp_hit_record(C.Structure):
         ("ray_offsets", C.c_void_p),
         ("ids", C.c_void_p),
         ("state", C.c_void_p),
+        ("counts", C.c_void_p),
         ("total", C.c_void_p),
         ("capacity", C.c_int64),
         ("id_cap", C.c_int32),
-        ("reserved", C.c_int32),
+        ("dense", C.c_int32),
     ]
 
 

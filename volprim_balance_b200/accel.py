@@ -65,21 +65,32 @@ class HitRecord:
     `with_state`: the primal also leaves every hit's colour and transmittance, and the adjoint's ray-major pass becomes
     the PRB recurrence alone), 8 per ray.  `usable()` reads two device counters (synchronises the stream once)."""
 
-    def __init__(self, n_rays: int, n_prims: int, capacity: int, id_cap: int, device, with_state: bool = False):
+    def __init__(self, n_rays: int, n_prims: int, capacity: int, id_cap: int, device, with_state: bool = False,
+                 dense: bool = False):
         self.n_rays, self.n_prims = n_rays, n_prims
-        self.capacity, self.id_cap = int(max(capacity, 1)), int(id_cap)
+        self.capacity, self.id_cap, self.dense = int(max(capacity, 1)), int(id_cap), bool(dense)
+        self.total = torch.zeros(2, dtype=torch.int64, device=device)
+        self._usable = None
+        if dense:
+            # hit-major block [id_cap, n_rays] in this record's own buffers: no compaction pass, coalesced replay
+            self.ray_offsets = None
+            self.ids = torch.empty((id_cap, n_rays), dtype=torch.int32, device=device)
+            self.state = torch.empty((id_cap, n_rays, 4), dtype=torch.float32, device=device)
+            self.counts = torch.empty(n_rays, dtype=torch.int32, device=device)
+            return
+        self.counts = None
         self.ray_offsets = torch.empty(n_rays + 1, dtype=torch.int64, device=device)
         self.ids = torch.empty(self.capacity, dtype=torch.int32, device=device)
         self.state = torch.empty((self.capacity, 4), dtype=torch.float32, device=device) if with_state else None
-        self.total = torch.zeros(2, dtype=torch.int64, device=device)
-        self._usable = None
 
     def to_c(self) -> vp_hit_record:
         r = vp_hit_record()
-        r.ray_offsets, r.ids = self.ray_offsets.data_ptr(), self.ids.data_ptr()
+        r.ray_offsets = self.ray_offsets.data_ptr() if self.ray_offsets is not None else None
+        r.ids = self.ids.data_ptr()
         r.state = self.state.data_ptr() if self.state is not None else None
+        r.counts = self.counts.data_ptr() if self.counts is not None else None
         r.total = self.total.data_ptr()
-        r.capacity, r.id_cap = self.capacity, self.id_cap
+        r.capacity, r.id_cap, r.dense = self.capacity, self.id_cap, int(self.dense)
         return r
 
     def totals(self):
@@ -93,12 +104,15 @@ class HitRecord:
         return self._usable
 
     def nbytes(self) -> int:
-        return self.ids.numel() * 4 + self.ray_offsets.numel() * 8 + (self.state.numel() * 4 if self.state is not None else 0)
+        return sum(t.numel() * t.element_size() for t in (self.ids, self.ray_offsets, self.state, self.counts) if t is not None)
 
     def lists(self):
         """Python view for tests: list of per-ray id arrays (host)."""
-        off = self.ray_offsets.cpu().numpy()
         ids = self.ids.cpu().numpy()
+        if self.dense:
+            cnt = self.counts.cpu().numpy()
+            return [ids[:cnt[r], r] for r in range(self.n_rays)]
+        off = self.ray_offsets.cpu().numpy()
         return [ids[off[r]:off[r + 1]] for r in range(self.n_rays)]
 
 
@@ -127,6 +141,7 @@ class EllipsoidAccel:
         self.built = False
         self.hits_per_ray_estimate = 48.0   # sizes the next hit record; follows the records actually produced
         self.state_budget_bytes = 8 << 30   # records above it keep ids only (4 B / hit) and the adjoint re-shades
+        self.dense_budget_bytes = 16 << 30  # a 1080p view at a cap of 128 hits takes 6.4 GB as a dense state record
 
     def close(self):
         if getattr(self, "_h", None):
@@ -227,15 +242,30 @@ class EllipsoidAccel:
     def set_option(self, name: str, value: int):
         _cabi.check(self._lib.vp_set_option(self._h, name.encode(), int(value)), self._h)
 
-    def new_record(self, n_rays: int, id_cap: int, capacity: int | None = None, with_state: bool | None = None) -> HitRecord:
-        """with_state=None: keep the per-hit (colour, transmittance) when the primitives carry colour coefficients and
-        the record stays below `state_budget_bytes` (default 8 GiB)."""
+    def new_record(self, n_rays: int, id_cap: int, capacity: int | None = None, with_state: bool | None = None,
+                   dense: bool | None = None) -> HitRecord:
+        """Kind of record (None = decide from the memory budgets, fastest first):
+          dense       hit-major [id_cap, n_rays] block with per-hit (colour, transmittance): no compaction pass, coalesced
+                      replay; 24 B * id_cap * n_rays incl. the adjoint's slot array (`dense_budget_bytes`, default 16 GiB)
+          rows+state  compressed rows, 20 B per hit (`state_budget_bytes`, default 8 GiB)
+          rows        compressed rows, 4 B per hit; the adjoint shades every hit again."""
         if capacity is None:
             capacity = int(n_rays * min(float(id_cap), self.hits_per_ray_estimate * 1.3 + 4.0)) + 4096
         capacity = min(capacity, (1 << 32) - 1)
+        if dense is None:
+            dense = with_state is not False and self.sh_floats > 0 and id_cap * n_rays * 24 <= self.dense_budget_bytes
+        if dense:
+            return HitRecord(n_rays, self.n, capacity, id_cap, self.device, dense=True)
         if with_state is None:
             with_state = capacity * 16 <= self.state_budget_bytes
         return HitRecord(n_rays, self.n, capacity, id_cap, self.device, with_state=with_state)
+
+    def record_bytes(self, n_rays: int, id_cap: int) -> int:
+        """Memory the record new_record() would choose for these rays takes (budgeting of multi-view renders)."""
+        entries = int(n_rays * min(float(id_cap), self.hits_per_ray_estimate * 1.3 + 4.0)) + 4096
+        if self.sh_floats > 0 and id_cap * n_rays * 24 <= self.dense_budget_bytes:
+            return id_cap * n_rays * 20 + n_rays * 4
+        return entries * (20 if entries * 16 <= self.state_budget_bytes else 4) + n_rays * 8
 
     def render_forward(self, params: vp_params, rays: RaySource, record=None, id_cap: int = 0,
                        want_beta: bool = True, want_nhits: bool = True) -> TraceResult:

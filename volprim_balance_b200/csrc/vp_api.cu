@@ -116,7 +116,7 @@ int vp_destroy(vp_ctx *ctx)
                          &ctx->nodes, &ctx->perm, &ctx->inv_perm, &ctx->leaf_lo, &ctx->leaf_hi, &ctx->keys[0],
                          &ctx->keys[1], &ctx->vals[0], &ctx->vals[1], &ctx->hist, &ctx->parent, &ctx->counters,
                          &ctx->bounds, &ctx->stats, &ctx->scan_tmp, &ctx->rec_dense, &ctx->rec_dense_state, &ctx->rec_counts, &ctx->rec_nhits,
-                         &ctx->adj_offsets, &ctx->adj_rank, &ctx->adj_state, &ctx->adj_ray, &ctx->adj_extra, &ctx->adj_items };
+                         &ctx->adj_offsets, &ctx->adj_rank, &ctx->adj_state, &ctx->adj_extra, &ctx->adj_items };
     for (DevBuffer *b : all) free_buf(*b);
     delete ctx;
     return VP_OK;

@@ -1228,15 +1228,30 @@ __device__ __forceinline__ void load_ray(const RaySrc &S, int64_t r, float3 &o, 
     maxt = S.maxt ? S.maxt[r] : FLT_MAX;
 }
 
-// per-hit state the ray-major pass of the gather adjoint leaves in the bucket of the hit primitive
+// What the ray-major pass of the gather adjoint leaves in the bucket of the hit primitive: one 32-byte entry per recorded
+// hit -- (d colour rgb, d alpha, ray direction xyz, ray index) -- written with ONE 256-bit store (a full sector: no
+// read-for-merge in L2) and read back with one 256-bit load.  Every recorded entry is written, zero gradient included,
+// so the buckets need no initialisation and no validity flags.
 struct GatherBuf {
     const uint32_t *offsets;   // [N + 1] bucket starts (exclusive prefix of the recorded hits per primitive)
-    const uint32_t *rank;      // [capacity] position of record entry e inside the bucket of its primitive
-    float4 *state;             // (dcol.rgb, dalpha) per bucket slot
-    uint32_t *ray;             // ray index per bucket slot; 0xFFFFFFFF = nothing written (ray skipped, zero gradient)
+    const uint32_t *rank;      // position of a record entry inside the bucket of its primitive (indexed like the ids)
+    float4 *entries;           // two float4 per bucket slot
     const int64_t *total;      // record validity: total[0] <= capacity && total[1] == 0
     int64_t capacity;
 };
+
+__device__ __forceinline__ void stg256(float4 *p, float4 a, float4 b)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x),
+                 "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ void bucket_store(const GatherBuf &gb, uint32_t slot, float dc0, float dc1, float dc2, float dalpha,
+                                             float3 d, int64_t r)
+{
+    stg256(gb.entries + 2ll * slot, make_float4(dc0, dc1, dc2, dalpha), make_float4(d.x, d.y, d.z, __uint_as_float((uint32_t)r)));
+}
 
 struct TraceArgs {
     int64_t R;
@@ -1500,13 +1515,11 @@ __device__ __forceinline__ void rf_scatter_hit(const TraceArgs &A, float4 g0, fl
 
 // gather formulation, ray-major pass: the per-hit coefficients go to the bucket of the hit primitive, at the slot the
 // counting pass assigned to this record entry (no atomics here: they would pin the loads of the replay loop in place)
-__device__ __forceinline__ void rf_bucket_hit(const TraceArgs &A, int orig, int64_t r, int64_t entry, RfCoeffs c)
+__device__ __forceinline__ void rf_bucket_hit(const TraceArgs &A, int orig, int64_t r, int64_t entry, float3 d, RfCoeffs c)
 {
     if (!(c.op * c.G < 0.9999f)) c.dalpha = 0.f;      // clamped alpha: no gradient to opacity / geometry
-    if (c.dalpha == 0.f && c.dcol[0] == 0.f && c.dcol[1] == 0.f && c.dcol[2] == 0.f) return;
     const uint32_t slot = __ldg(A.gb.offsets + orig) + __ldg(A.gb.rank + entry);
-    A.gb.state[slot] = make_float4(c.dcol[0], c.dcol[1], c.dcol[2], c.dalpha);
-    A.gb.ray[slot] = (uint32_t)r;
+    bucket_store(A.gb, slot, c.dcol[0], c.dcol[1], c.dcol[2], c.dalpha, d, r);
 }
 
 // one tomography interaction of the adjoint; returns T.  L stays state_in until the ray escapes (tomo:92-101).
@@ -1634,7 +1647,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE != ADJ_WALK ? VP_REPLAY_BL
             // bucket mode evaluates every hit from the ray's ORIGINAL origin (rf_eval_far): no exact entry distance, no
             // origin advance -- the list already fixes which primitives are hit and in which order
             const RfCoeffs c = rf_adjoint_coeffs<KERNEL, D, MODE == ADJ_REPLAY_BUCKET>(S, pos, o, d, g0, g1, Rm, is, beta, g, L, Y);
-            if constexpr (MODE == ADJ_REPLAY_BUCKET) rf_bucket_hit(A, __float_as_int(g1.w), r, entry, c);
+            if constexpr (MODE == ADJ_REPLAY_BUCKET) rf_bucket_hit(A, __float_as_int(g1.w), r, entry, d, c);
             else rf_scatter_hit<KERNEL, D>(A, g0, g1, g2, Rm, c, Y);
             T = c.T;
         } else
@@ -1651,6 +1664,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, MODE != ADJ_WALK ? VP_REPLAY_BL
         return true;
     };
 
+    if constexpr (MODE == ADJ_REPLAY_BUCKET) {
+        if (in_range && !alive) {      // rf:111-112 skips the ray; its bucket entries still have to exist (as zeros)
+            for (int64_t e = A.rec_offsets[r]; e < A.rec_offsets[r + 1]; ++e)
+                bucket_store(A.gb, __ldg(A.gb.offsets + A.rec_ids[e]) + __ldg(A.gb.rank + e), 0.f, 0.f, 0.f, 0.f, d, r);
+        }
+    }
     if constexpr (REPLAY) {
         if (alive) {
             // this ray's list: element k at list[k * stride]
@@ -1732,7 +1751,7 @@ constexpr uint32_t GATHER_CHUNK = VP_GATHER_CHUNK;
 // range one warp for its first chunk and adds the sums with plain read-modify-writes; the EXTRA pass runs one warp per
 // further chunk of the big buckets and adds with reductions (few: 59 per 256 hits instead of 27 per hit).
 #ifndef VP_GATHER_BLOCKS
-#define VP_GATHER_BLOCKS 5
+#define VP_GATHER_BLOCKS 4
 #endif
 template <int KERNEL, int D, bool EXTRA>
 __global__ void __launch_bounds__(128, VP_GATHER_BLOCKS) k_adjoint_gather(GatherArgs A)
@@ -1762,8 +1781,7 @@ __global__ void __launch_bounds__(128, VP_GATHER_BLOCKS) k_adjoint_gather(Gather
     const uint32_t size = __ldg(A.gb.offsets + p + 1) - base;
     if (first >= size) return;
     const uint32_t cnt = min(size - first, GATHER_CHUNK);
-    const float4 *bstate = A.gb.state + base + first;
-    const uint32_t *bray = A.gb.ray + base + first;
+    const float4 *bent = A.gb.entries + 2ll * (base + first);
     const float *rec = A.data10 + 10 * p;
     const float4 g0 = make_float4(__ldg(rec), __ldg(rec + 1), __ldg(rec + 2), A.attr ? __ldg(A.attr + p) : 1.f);
     const float4 g1 = make_float4(__ldg(rec + 3), __ldg(rec + 4), __ldg(rec + 5), 0.f);
@@ -1775,22 +1793,19 @@ __global__ void __launch_bounds__(128, VP_GATHER_BLOCKS) k_adjoint_gather(Gather
 
     // one entry ahead: the bucket entry of the next round is in flight while this one is evaluated
     uint32_t i = lane;
-    float4 st_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t ray_next = 0xffffffffu;
-    if (i < cnt) { ray_next = __ldcs(bray + i); st_next = __ldcs(bstate + i); }
+    float4 ea_next = make_float4(0.f, 0.f, 0.f, 0.f), eb_next = ea_next;
+    if (i < cnt) ldg256(bent + 2ll * i, ea_next, eb_next);
     bool any = false;
     while (i < cnt) {
-        const float4 st = st_next;
-        const uint32_t r = ray_next;
+        const float4 st = ea_next, eb = eb_next;
         i += 32;
-        if (i < cnt) { ray_next = __ldcs(bray + i); st_next = __ldcs(bstate + i); }
-        if (r == 0xffffffffu) continue;             // slot never written: the ray was skipped or the hit carries no gradient
+        if (i < cnt) ldg256(bent + 2ll * i, ea_next, eb_next);
+        const bool has_col = st.x != 0.f || st.y != 0.f || st.z != 0.f;
+        if (!has_col && st.w == 0.f) continue;      // a hit without gradient (or a ray without): nothing to add
         any = true;
-        float3 o, d;
-        float maxt;
-        load_ray(A.src, r, o, d, maxt);
+        const float3 d = make_float3(eb.x, eb.y, eb.z);
         if constexpr (D >= 0) {
-            if (st.x != 0.f || st.y != 0.f || st.z != 0.f) {
+            if (has_col) {
                 float Y[NB > 0 ? NB : 1];
                 sh_basis<(D >= 0 ? D : 0)>(d, Y);
 #pragma unroll
@@ -1802,6 +1817,14 @@ __global__ void __launch_bounds__(128, VP_GATHER_BLOCKS) k_adjoint_gather(Gather
             }
         }
         if (st.w != 0.f) {
+            // any point of the ray serves as the origin (rf_eval_far re-bases): the sensor's position, or the ray's own
+            // origin for an explicit batch
+            float3 o;
+            if (A.src.has_cam) o = make_float3(A.src.cam.to_world[3], A.src.cam.to_world[7], A.src.cam.to_world[11]);
+            else {
+                const int64_t r = __float_as_uint(eb.w);
+                o = make_float3(__ldg(A.src.o + 3 * r), __ldg(A.src.o + 3 * r + 1), __ldg(A.src.o + 3 * r + 2));
+            }
             const RfEval e = rf_eval_far<KERNEL>(o, d, g0, g1, Rm);
             acc[C] = fmaf(st.w, e.G, acc[C]);                       // d opacity
             float3 v, wv;
@@ -1900,6 +1923,80 @@ __global__ void __launch_bounds__(256) k_bucket_ranks(const int32_t *__restrict_
     }
 }
 
+// the same over a DENSE hit-major record ([id_cap][n_rays], entry (k, r) valid for k < counts[r]): one thread per ray,
+// reads and rank writes coalesced across the warp
+__global__ void __launch_bounds__(256) k_bucket_ranks_dense(const int32_t *__restrict__ ids, const uint32_t *__restrict__ ray_counts,
+                                                            int64_t n_rays, const int64_t *__restrict__ total, int64_t capacity,
+                                                            uint32_t *__restrict__ counts, uint32_t *__restrict__ rank)
+{
+    if (total[0] > capacity || total[1] != 0) return;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const uint32_t c = ray_counts[r];
+    for (uint32_t k = 0; k < c; ++k) {
+        const int64_t e = (int64_t)k * n_rays + r;
+        rank[e] = atomicAdd(counts + ids[e], 1u);
+    }
+}
+
+// Ray-major pass over a dense record carrying the per-hit (colour, transmittance): one thread per ray, every load
+// coalesced (lane = ray, same hit index); the PRB recurrences of volprim_rf.py:137-165 alone.
+// one hit of the recurrences of volprim_rf.py:137-165 from its recorded (colour, transmittance)
+__device__ __forceinline__ void prb_step(float4 st, const float (&g)[3], float (&L)[3], float &beta, float &dalpha, float (&dcol)[3])
+{
+    const float T = st.w, omt = 1.f - T;
+    const float col[3] = { st.x, st.y, st.z };
+    dalpha = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float le = beta * omt * col[ch];
+        const bool lef = isfinite(le);
+        if (!lef) le = 0.f;
+        L[ch] -= le;                                  // rf:145 (adjoint branch)
+        const float lo = le + L[ch] * T / T;          // rf:156-159
+        dcol[ch] = 0.f;
+        if (isfinite(lo)) {                           // rf:160
+            if (lef) {
+                dalpha += g[ch] * beta * col[ch];
+                if (col[ch] > 0.f) dcol[ch] = g[ch] * beta * omt;
+            }
+            dalpha -= g[ch] * L[ch] / T;
+        }
+    }
+    if (!(T > 1.f - 0.9999f)) dalpha = 0.f;           // alpha was clamped (rf:76): no gradient to opacity / geometry
+    beta *= T;
+}
+
+__global__ void __launch_bounds__(128) k_adjoint_rows_dense(RaySrc src, int64_t R, int32_t image_w, int32_t image_h, const float *__restrict__ dL,
+                                                            const float *__restrict__ state_in,
+                                                            const uint32_t *__restrict__ ray_counts,
+                                                            const int32_t *__restrict__ ids, const float4 *__restrict__ hit_state,
+                                                            GatherBuf gb)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= R || !record_usable(gb)) return;
+    const int64_t r = ray_index(t, image_w, image_h);      // 8x4 pixel tiles: neighbours hit the same primitives
+    const float g[3] = { dL[3 * r], dL[3 * r + 1], dL[3 * r + 2] };
+    const bool live = g[0] != 0.f || g[1] != 0.f || g[2] != 0.f;      // rf:111-112: a ray without gradient leaves zero entries
+    float L[3] = { state_in[3 * r], state_in[3 * r + 1], state_in[3 * r + 2] };
+    float beta = 1.f;
+    float3 o, d;
+    float maxt;
+    load_ray(src, r, o, d, maxt);
+    const uint32_t n = ray_counts[r];
+    float4 st_next = n ? __ldcs(hit_state + r) : make_float4(0.f, 0.f, 0.f, 1.f);
+    for (uint32_t k = 0; k < n; ++k) {
+        const int64_t e = (int64_t)k * R + r;
+        const float4 st = st_next;
+        if (k + 1 < n) st_next = __ldcs(hit_state + e + R);
+        const uint32_t slot = __ldg(gb.offsets + __ldcs(ids + e)) + __ldcs(gb.rank + e);
+        float dalpha, dcol[3];
+        prb_step(st, g, L, beta, dalpha, dcol);
+        if (!live) { dalpha = 0.f; dcol[0] = dcol[1] = dcol[2] = 0.f; }
+        bucket_store(gb, slot, dcol[0], dcol[1], dcol[2], dalpha, d, r);
+    }
+}
+
 // extra work items of the primitive-major pass: ceil(size / CHUNK) - 1 per bucket
 __global__ void k_extra_counts(const uint32_t *__restrict__ offsets, int64_t n, uint32_t *__restrict__ extra)
 {
@@ -1920,17 +2017,23 @@ __global__ void k_extra_items(const uint32_t *__restrict__ extra_offsets, int64_
 // ---- hit records: dense hit-major scratch -> compressed rows ----------------------------------------------------------
 // per-ray entry counts of a band (clamped at the record's per-ray cap) + number of rays whose list was cut
 __global__ void k_record_counts(const uint32_t *__restrict__ nhits, int64_t n, int32_t cap, uint32_t *__restrict__ counts,
-                                int64_t *__restrict__ total)
+                                int64_t *__restrict__ total, bool sum_entries)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool cut = false;
+    uint32_t c = 0;
     if (r < n) {
         const uint32_t h = nhits[r];
         cut = h > (uint32_t)cap;
-        counts[r] = cut ? (uint32_t)cap : h;
+        c = cut ? (uint32_t)cap : h;
+        counts[r] = c;
     }
     const unsigned m = __ballot_sync(0xffffffffu, cut);
     if (m && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)(total + 1), (unsigned long long)__popc(m));
+    if (sum_entries) {      // dense records: total[0] = number of entries (compressed rows get it from their scan)
+        const uint32_t s = __reduce_add_sync(0xffffffffu, c);
+        if (s && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)total, (unsigned long long)s);
+    }
 }
 
 // Dense hit-major block -> compressed rows.  One warp per 32 consecutive rays; the block is read coalesced (lane = ray,
@@ -1988,50 +2091,66 @@ __global__ void __launch_bounds__(64) k_compact_state(const float4 *__restrict__
 }
 
 // Ray-major pass of the gather adjoint when the record carries the per-hit (colour, transmittance): the PRB recurrences
-// of volprim_rf.py:137-165 alone -- no primitive is loaded, nothing is intersected or shaded again.  One thread per ray
-// walks its row of the record and leaves (d colour, d alpha) in the bucket slot of every hit.
-__global__ void __launch_bounds__(256) k_adjoint_rows(int64_t R, const float *__restrict__ dL, const float *__restrict__ state_in,
-                                                      const int64_t *__restrict__ offsets, const int32_t *__restrict__ ids,
-                                                      const float4 *__restrict__ hit_state, GatherBuf gb, vp_params P)
+// of volprim_rf.py:137-165 alone -- no primitive is loaded, nothing is intersected or shaded again.  A warp owns 32
+// consecutive rays.  Their rows of the record are staged through shared memory 16 entries at a time (two rows per
+// step, every row segment read coalesced); lane l then walks the staged entries of ray l and leaves (d colour, d alpha)
+// in the bucket slot of every hit.
+constexpr int ROWS_K = 16;          // entries of a row staged per round
+constexpr int ROWS_WARPS = 2;
+__global__ void __launch_bounds__(32 * ROWS_WARPS) k_adjoint_rows(RaySrc src, int64_t R, const float *__restrict__ dL,
+                                                                  const float *__restrict__ state_in,
+                                                                  const int64_t *__restrict__ offsets,
+                                                                  const int32_t *__restrict__ ids,
+                                                                  const float4 *__restrict__ hit_state, GatherBuf gb)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R || !record_usable(gb)) return;
-    const float g[3] = { dL[3 * r], dL[3 * r + 1], dL[3 * r + 2] };
-    if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) return;                        // rf:111-112
-    float L[3] = { state_in[3 * r], state_in[3 * r + 1], state_in[3 * r + 2] };
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ float4 s_state[ROWS_WARPS][32][ROWS_K + 1];
+    __shared__ int32_t s_id[ROWS_WARPS][32][ROWS_K + 1];
+    __shared__ uint32_t s_rank[ROWS_WARPS][32][ROWS_K + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t r0 = ((int64_t)blockIdx.x * ROWS_WARPS + wid) * 32;
+    if (r0 >= R || !record_usable(gb)) return;
+    const int64_t r = r0 + lane;
+    float g[3] = { 0.f, 0.f, 0.f }, L[3] = { 0.f, 0.f, 0.f };
+    float3 o = make_float3(0.f, 0.f, 0.f), d = make_float3(0.f, 0.f, 1.f);
+    int64_t e0 = 0;
+    uint32_t n = 0;
+    if (r < R) {
+        float maxt;
+        load_ray(src, r, o, d, maxt);
+        g[0] = dL[3 * r]; g[1] = dL[3 * r + 1]; g[2] = dL[3 * r + 2];
+        e0 = offsets[r];
+        n = (uint32_t)(offsets[r + 1] - e0);
+        L[0] = state_in[3 * r]; L[1] = state_in[3 * r + 1]; L[2] = state_in[3 * r + 2];
+    }
+    const bool live = g[0] != 0.f || g[1] != 0.f || g[2] != 0.f;      // rf:111-112: a ray without gradient leaves zero entries
     float beta = 1.f;
-    const int64_t e0 = offsets[r], e1 = offsets[r + 1];
-    const float t_clamped = 1.f - 0.9999f;        // T of a hit whose alpha was clamped (rf:76): no gradient to opacity / geometry
-    float4 st_next = e0 < e1 ? __ldcs(hit_state + e0) : make_float4(0.f, 0.f, 0.f, 1.f);
-    for (int64_t e = e0; e < e1; ++e) {
-        const float4 st = st_next;
-        if (e + 1 < e1) st_next = __ldcs(hit_state + e + 1);
-        const float T = st.w, omt = 1.f - T;
-        const float col[3] = { st.x, st.y, st.z };
-        float dalpha = 0.f, dcol[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            float le = beta * omt * col[ch];
-            const bool lef = isfinite(le);
-            if (!lef) le = 0.f;
-            L[ch] -= le;                                  // rf:145 (adjoint branch)
-            const float lo = le + L[ch] * T / T;          // rf:156-159
-            dcol[ch] = 0.f;
-            if (isfinite(lo)) {                           // rf:160
-                if (lef) {
-                    dalpha += g[ch] * beta * col[ch];
-                    if (col[ch] > 0.f) dcol[ch] = g[ch] * beta * omt;
-                }
-                dalpha -= g[ch] * L[ch] / T;
+    const uint32_t nmax = __reduce_max_sync(FULL, n);
+    const int half = lane >> 4, sub = lane & 15;
+    for (uint32_t k0 = 0; k0 < nmax; k0 += ROWS_K) {
+        // stage entries k0 .. k0 + 15 of all 32 rows: lanes 0-15 take row 2 i, lanes 16-31 row 2 i + 1
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int j = 2 * i + half;
+            const uint32_t nj = __shfl_sync(FULL, n, j);
+            const int64_t ej = __shfl_sync(FULL, e0, j);
+            if (k0 + sub < nj) {
+                const int64_t e = ej + k0 + sub;
+                s_state[wid][j][sub] = __ldcs(hit_state + e);
+                s_id[wid][j][sub] = __ldcs(ids + e);
+                s_rank[wid][j][sub] = __ldcs(gb.rank + e);
             }
         }
-        if (!(T > t_clamped)) dalpha = 0.f;
-        if (dalpha != 0.f || dcol[0] != 0.f || dcol[1] != 0.f || dcol[2] != 0.f) {
-            const uint32_t slot = __ldg(gb.offsets + __ldcs(ids + e)) + __ldcs(gb.rank + e);
-            gb.state[slot] = make_float4(dcol[0], dcol[1], dcol[2], dalpha);
-            gb.ray[slot] = (uint32_t)r;
+        __syncwarp();
+        const uint32_t kn = n > k0 ? min((uint32_t)ROWS_K, n - k0) : 0u;
+        for (uint32_t k = 0; k < kn; ++k) {
+            const uint32_t slot = __ldg(gb.offsets + s_id[wid][lane][k]) + s_rank[wid][lane][k];
+            float dalpha, dcol[3];
+            prb_step(s_state[wid][lane][k], g, L, beta, dalpha, dcol);
+            if (!live) { dalpha = 0.f; dcol[0] = dcol[1] = dcol[2] = 0.f; }
+            bucket_store(gb, slot, dcol[0], dcol[1], dcol[2], dalpha, d, r);
         }
-        beta *= T;
+        __syncwarp();
     }
 }
 
@@ -2200,8 +2319,9 @@ RaySrc slice_ray_src(const RaySrc &s, int64_t first)
 
 int check_record(vp_ctx *ctx, const vp_hit_record *rec, const char *who)
 {
-    if (!rec->ray_offsets || !rec->ids || !rec->total)
-        return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record arrays (ray_offsets, ids, total) are required");
+    if (!rec->ids || !rec->total || (rec->dense ? (!rec->counts || !rec->state) : !rec->ray_offsets))
+        return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record arrays are missing (rows: ray_offsets, ids, total; dense: ids, "
+                                                             "state, counts, total)");
     if (rec->capacity <= 0 || rec->capacity >= (1ll << 32) || rec->id_cap <= 0)
         return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record needs 0 < capacity < 2^32 and id_cap > 0");
     if (rec->state && (uintptr_t)rec->state % 16) return vp_fail(ctx, VP_E_INVALID, std::string(who) + ": record state must be 16-byte aligned");
@@ -2306,8 +2426,25 @@ int vp_render_forward_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sour
         VP_CUDA_CHECK(ctx, cudaGetLastError());
         return VP_OK;
     }
-    // ---- recording: row bands bound the dense hit-major scratch ----
     VP_CUDA_CHECK(ctx, cudaMemsetAsync(rec->total, 0, 2 * sizeof(int64_t), st));
+    if (rec->dense) {
+        // dense hit-major record in the caller's buffers ([id_cap][n_rays] ids and (colour, T)): ONE launch, nothing is
+        // moved afterwards, and the adjoint reads it coalesced.  5x the bytes of compressed rows, for the fastest step.
+        if (P.integrator != VP_INTEGRATOR_RF) return vp_fail(ctx, VP_E_INVALID, "vp_render_forward: dense state records are a volprim_rf feature");
+        if (R == 0) return VP_OK;
+        uint32_t *nh = nhits;
+        if (!nh) {
+            if ((rc = vp_ensure(ctx, ctx->rec_nhits, sizeof(uint32_t) * (size_t)R))) return rc;
+            nh = (uint32_t *)ctx->rec_nhits.ptr;
+        }
+        A.R = R; A.src = src; A.nhits = nh;
+        A.ids = rec->ids; A.hit_state = (float4 *)rec->state; A.cap = rec->id_cap; A.rs = 1; A.hs = R;
+        if ((rc = dispatch<0>(ctx, S, P, A, nullptr, st))) return rc;
+        k_record_counts<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(nh, R, rec->id_cap, rec->counts, rec->total, true);
+        VP_CUDA_CHECK(ctx, cudaGetLastError());
+        return VP_OK;
+    }
+    // ---- recording: row bands bound the dense hit-major scratch ----
     if (R == 0) {
         VP_CUDA_CHECK(ctx, cudaMemsetAsync(rec->ray_offsets, 0, sizeof(int64_t), st));
         return VP_OK;
@@ -2358,7 +2495,7 @@ int vp_render_forward_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sour
         B.hit_state = with_state ? (float4 *)ctx->rec_dense_state.ptr : nullptr;
         if ((rc = dispatch<0>(ctx, S, Pb, B, nullptr, st))) return rc;
         const unsigned blocks = (unsigned)((cnt + 255) / 256), cblocks = (unsigned)((cnt + 127) / 128);
-        k_record_counts<<<blocks, 256, 0, st>>>(B.nhits, cnt, cap, (uint32_t *)ctx->rec_counts.ptr, rec->total);
+        k_record_counts<<<blocks, 256, 0, st>>>(B.nhits, cnt, cap, (uint32_t *)ctx->rec_counts.ptr, rec->total, false);
         vpscan::exclusive_scan<unsigned long long>((const uint32_t *)ctx->rec_counts.ptr, cnt,
                                                    (unsigned long long *)rec->ray_offsets + first,
                                                    (unsigned long long *)ctx->scan_tmp.ptr, (unsigned long long *)rec->total,
@@ -2402,8 +2539,7 @@ GatherBuf gather_buf(vp_ctx *ctx, const vp_hit_record *rec)
     GatherBuf gb;
     gb.offsets = (const uint32_t *)ctx->adj_offsets.ptr;
     gb.rank = (const uint32_t *)ctx->adj_rank.ptr;
-    gb.state = (float4 *)ctx->adj_state.ptr;
-    gb.ray = (uint32_t *)ctx->adj_ray.ptr;
+    gb.entries = (float4 *)ctx->adj_state.ptr;
     gb.total = rec->total;
     gb.capacity = rec->capacity;
     return gb;
@@ -2436,17 +2572,21 @@ int vp_adjoint_begin_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sourc
         if ((rc = vp_ensure(ctx, ctx->adj_offsets, sizeof(uint32_t) * (size_t)(n + 1)))) return rc;
         if ((rc = vp_ensure(ctx, ctx->adj_extra, sizeof(uint32_t) * (size_t)(n + 1)))) return rc;
         if ((rc = vp_ensure(ctx, ctx->adj_items, sizeof(uint32_t) * (size_t)max_extra))) return rc;
-        if ((rc = vp_ensure(ctx, ctx->adj_rank, sizeof(uint32_t) * (size_t)rec->capacity))) return rc;
-        if ((rc = vp_ensure(ctx, ctx->adj_state, sizeof(float4) * (size_t)rec->capacity))) return rc;
-        if ((rc = vp_ensure(ctx, ctx->adj_ray, sizeof(uint32_t) * (size_t)rec->capacity))) return rc;
+        // (a dense record addresses its rank array like its ids: [id_cap][n_rays])
+        const int64_t rank_slots = rec->dense ? (int64_t)rec->id_cap * R : rec->capacity;
+        if ((rc = vp_ensure(ctx, ctx->adj_rank, sizeof(uint32_t) * (size_t)(rank_slots > 0 ? rank_slots : 1)))) return rc;
+        if ((rc = vp_ensure(ctx, ctx->adj_state, 2 * sizeof(float4) * (size_t)rec->capacity))) return rc;
         if ((rc = vp_ensure(ctx, ctx->scan_tmp, sizeof(uint64_t) * (size_t)(vpscan::n_tiles(n) + 1)))) return rc;
         uint32_t *offsets = (uint32_t *)ctx->adj_offsets.ptr, *extra = (uint32_t *)ctx->adj_extra.ptr;
         VP_CUDA_CHECK(ctx, cudaMemsetAsync(offsets, 0, sizeof(uint32_t) * (size_t)(n + 1), st));
-        VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->adj_ray.ptr, 0xff, sizeof(uint32_t) * (size_t)rec->capacity, st));
         if (n > 0) {
             int64_t blocks = (rec->capacity + 255) / 256;
             if (blocks > 148 * 32) blocks = 148 * 32;
-            k_bucket_ranks<<<(unsigned)blocks, 256, 0, st>>>(rec->ids, rec->total, rec->capacity, offsets, (uint32_t *)ctx->adj_rank.ptr);
+            if (rec->dense)
+                k_bucket_ranks_dense<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(rec->ids, rec->counts, R, rec->total, rec->capacity,
+                                                                                 offsets, (uint32_t *)ctx->adj_rank.ptr);
+            else
+                k_bucket_ranks<<<(unsigned)blocks, 256, 0, st>>>(rec->ids, rec->total, rec->capacity, offsets, (uint32_t *)ctx->adj_rank.ptr);
             vpscan::exclusive_scan<uint32_t>(offsets, n, offsets, (uint32_t *)ctx->scan_tmp.ptr, nullptr, offsets + n, st);
             k_extra_counts<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(offsets, n, extra);
             vpscan::exclusive_scan<uint32_t>(extra, n, extra, (uint32_t *)ctx->scan_tmp.ptr, nullptr, extra + n, st);
@@ -2455,9 +2595,15 @@ int vp_adjoint_begin_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sourc
     }
     A.gb = gather_buf(ctx, rec);
     if (R == 0) return VP_OK;
+    if (P.integrator == VP_INTEGRATOR_RF && rec->dense) {
+        k_adjoint_rows_dense<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(src, R, P.image_width, P.image_height, dL, state_in, rec->counts,
+                                                                         rec->ids, (const float4 *)rec->state, A.gb);
+        VP_CUDA_CHECK(ctx, cudaGetLastError());
+        return VP_OK;
+    }
     if (P.integrator == VP_INTEGRATOR_RF && rec->state) {
-        k_adjoint_rows<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(R, dL, state_in, rec->ray_offsets, rec->ids,
-                                                                   (const float4 *)rec->state, A.gb, P);
+        k_adjoint_rows<<<(unsigned)((R + 32 * ROWS_WARPS - 1) / (32 * ROWS_WARPS)), 32 * ROWS_WARPS, 0, st>>>(
+            src, R, dL, state_in, rec->ray_offsets, rec->ids, (const float4 *)rec->state, A.gb);
         VP_CUDA_CHECK(ctx, cudaGetLastError());
         return VP_OK;
     }

@@ -288,7 +288,7 @@ def traverse(scene: Scene) -> SceneParameters:
 # render
 # ---------------------------------------------------------------------------------------------------
 REUSE_PRIMAL_RECORDS = True      # False: always re-trace in the backward pass, as RBIntegrator.render_backward does
-RECORD_BUDGET_BYTES = 8 << 30    # hit records kept between the primal and the backward pass, summed over the views of a
+RECORD_BUDGET_BYTES = 32 << 30   # hit records kept between the primal and the backward pass, summed over the views of a
                                  # render() call; views beyond the budget are re-traced in the backward pass
 
 
@@ -406,8 +406,7 @@ def _render_primal_impl(scene, sensor, integrator, seed, spp, jitter, record, ro
         rays = RaySource(camera=s.vp_camera(), spp=spp, jitter=jit, rows=band)
         want = bool(record)
         if want:   # budget over the views of this call
-            entries = int(rays.n_rays * (acc.hits_per_ray_estimate * 1.3 + 4.0))
-            need = entries * (20 if entries * 16 <= acc.state_budget_bytes else 4) + rays.n_rays * 8
+            need = acc.record_bytes(rays.n_rays, integrator._cap())
             want = need <= budget
             budget -= need if want else 0
         res = acc.render_forward(params, rays, record=want, id_cap=integrator._cap(), want_beta=False, want_nhits=False)
