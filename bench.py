@@ -613,7 +613,8 @@ def run_train_step(args, torch, dist, vp, training, parallel, Ellipsoid, wl, clo
     opt.set_learning_rate({"centers": 1e-4, "scales": 1e-4, "quats": 1e-4, "opacities": 1e-2, "sh_coeffs": 1e-3})
     opt.set_bounds("scales", lower=1e-6)
     opt.set_bounds("opacities", lower=1e-6, upper=1.0 - 1e-6)
-    step = training.RefineStep(scene, sensors, targets, opt, n_chunks=args.train_chunks, rebuild=args.train_rebuild)
+    step = training.RefineStep(scene, sensors, targets, opt, n_chunks=args.train_chunks, rebuild=args.train_rebuild,
+                               rebuild_every=args.train_rebuild_every)
     losses = []
     for _ in range(2):
         losses.append(float(step.step()[0]))
@@ -640,7 +641,8 @@ def run_train_step(args, torch, dist, vp, training, parallel, Ellipsoid, wl, clo
     return {"workload": f"refine_3dg_dataset-style step (BASELINE configs[3]): {wl['n']} Gaussian primitives SH3, a fixed batch of "
                         f"{len(sensors)} views of {W}x{H} per step sharded by view over {world} GPU(s); per view forward (recording) + "
                         f"gather adjoint, L1 loss; gradient all-reduce in {len(step.ranges)} primitive ranges overlapped with the last "
-                        f"view's accumulation; BoundedAdam; LBVH {args.train_rebuild}",
+                        f"view's accumulation; fused L1 loss + gradient; BoundedAdam; LBVH {args.train_rebuild}"
+                        + (f" (full build every {args.train_rebuild_every} steps)" if args.train_rebuild == "refit" else ""),
             "scaling": "strong", "views_per_step": len(sensors), "views_per_gpu": len(mine), "ms_per_step": ms,
             "views_per_s": len(sensors) / (ms * 1e-3), "Mrays_per_s": len(sensors) * W * H / (ms * 1e-3) / 1e6,
             "allreduce_bytes": step.bucket.flat.numel() * 4 if world > 1 else 0, "allreduce_ranges": len(step.ranges),
@@ -662,7 +664,9 @@ def main():
     ap.add_argument("--warmup-full", action="store_true")
     ap.add_argument("--train-steps", type=int, default=6)
     ap.add_argument("--train-chunks", type=int, default=4)
-    ap.add_argument("--train-rebuild", default="rebuild", choices=["rebuild", "refit"])
+    ap.add_argument("--train-rebuild", default="refit", choices=["rebuild", "refit"],
+                    help="LBVH after every optimiser step: full rebuild, or refit with a full build every --train-rebuild-every steps")
+    ap.add_argument("--train-rebuild-every", type=int, default=8)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if not args.views_per_step:

@@ -237,6 +237,13 @@ VP_API int vp_bounded_adam_step(int64_t n, float *param, const float *grad, floa
                                 double beta2, double eps, int has_lower, float lower, int has_upper, float upper,
                                 void *stream);
 
+/* l1(reference, image) (volprim/optimizers.py:170-174), the seed dr.backward(loss) hands the render op (d loss / d image
+ * = sign(image - reference) / n_total) and the squared error of psnr() (:180-186) in one pass over n floats.  ADDS
+ * sum |diff| / n_total to sums[0] and sum diff^2 / n_total to sums[1] (device, caller-zeroed); n_total = element count of
+ * the whole batch film, so that the views of a batch can be processed one at a time. */
+VP_API int vp_l1_loss_grad(int64_t n, const float *image, const float *reference, double n_total, float *d_image, float *sums,
+                           void *stream);
+
 /* Introspection for tests: copies the BVH node array (16 floats per internal node, layout in
  * csrc/vp_build.cu) and the sorted->original index into caller device buffers (either may be NULL);
  * *n_internal receives the internal-node count (N-1). */

@@ -21,7 +21,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "volprim_cuda.h")).read()
-    declared = set(re.findall(r"VP_API[^;(]*?\b(vp_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"VP_API[^;(]*?\b(vp_[a-z0-9_]+)\s*\(", hdr))
     assert len(declared) >= 21
     assert declared == set(_cabi.SIGNATURES), "ctypes table and header disagree"
     lib = _cabi.load_library()

@@ -144,14 +144,15 @@ def test_training_step_equals_autograd_path_single_gpu():
         l = (targets2[i] - img).abs().sum() / n_pix
         l.backward()
         total += float(l)
-    assert abs(total - float(loss)) < 1e-6
-    g = bucket.data.view(-1, 10)
+    assert abs(total - float(loss)) < 2e-6
+    g_data, g_attr, g_sh = bucket.gather()
+    g = g_data.view(-1, 10)
     from tests.parity_utils import grad_close
     grad_close(g[:, 0:3].cpu().numpy(), opt2["centers"].grad.cpu().numpy(), rtol=1e-4, what="centers")
     grad_close(g[:, 3:6].cpu().numpy(), opt2["scales"].grad.cpu().numpy(), rtol=1e-4, what="scales")
     grad_close(g[:, 6:10].cpu().numpy(), opt2["quats"].grad.cpu().numpy(), rtol=1e-4, what="quats")
-    grad_close(bucket.attr.cpu().numpy(), opt2["opacities"].grad.cpu().numpy(), rtol=1e-4, what="opacities")
-    grad_close(bucket.sh.cpu().numpy(), opt2["sh_coeffs"].grad.cpu().numpy(), rtol=1e-4, what="sh")
+    grad_close(g_attr.cpu().numpy(), opt2["opacities"].grad.cpu().numpy(), rtol=1e-4, what="opacities")
+    grad_close(g_sh.cpu().numpy(), opt2["sh_coeffs"].grad.cpu().numpy(), rtol=1e-4, what="sh")
     # and a few full steps reduce the loss
     first = float(step.step()[0])
     for _ in range(4):

@@ -31,15 +31,25 @@ def test_packed_gradient_segments_are_aligned_and_ranges_tile():
         back = parallel.unpack_gradients(flat, g, keys)
         assert all(torch.equal(back[k], g[k]) for k in g)
         assert all((back[k].data_ptr() - flat.data_ptr()) % 16 == 0 for k in g)      # any N, aligned slices
-        b = parallel.GradientBucket(n, 27, "cpu")
-        assert all((t.data_ptr() - b.flat.data_ptr()) % 16 == 0 for t in b.tensors())
-        assert b.data.numel() == n * 10 and b.attr.numel() == n and b.sh.numel() == n * 27
         for chunks in (1, 3, 4, 64):
             r = parallel.chunk_ranges(n, chunks)
             assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == c[0] for a, c in zip(r, r[1:]))
             assert all(p0 % 4 == 0 for p0, _ in r)
-            views = [b.chunk_views(p0, p1) for p0, p1 in r]
-            assert sum(v[0].numel() for v in views) == n * 10 and sum(v[2].numel() for v in views) == n * 27
+            b = parallel.GradientBucket(n, 27, "cpu", ranges=r)
+            base = b.flat.data_ptr()
+            for c, (p0, p1) in enumerate(r):
+                views = b.chunk_views(c)
+                assert [v.numel() for v in views] == [(p1 - p0) * 10, p1 - p0, (p1 - p0) * 27]
+                assert all((v.data_ptr() - base) % 16 == 0 for v in views)            # aligned segments for any N
+                # the shifted base pointers put global row p0 at the start of the range's own segments
+                gd, ga, gs = b.pointers(c)
+                assert (gd + 40 * p0, ga + 4 * p0, gs + 108 * p0) == tuple(v.data_ptr() for v in views)
+                assert gd % 8 == 0 and ga % 4 == 0
+                views[0].fill_(c + 1)
+            data, attr, sh = b.gather()
+            assert data.numel() == n * 10 and attr.numel() == n and sh.numel() == n * 27
+            assert all(bool((data[10 * p0:10 * p1] == c + 1).all()) for c, (p0, p1) in enumerate(r))
+            assert sum(b.chunk_flat(c).numel() for c in range(len(r))) == b.flat.numel() or n < 4
 
 
 def _free_port():
@@ -60,13 +70,17 @@ def _worker(rank, ws, port, q):
         red = parallel.allreduce_gradients(g)
         ok = bool((red["data"] == 3).all() and torch.equal(red["opacities"], torch.arange(n, dtype=torch.float32) * 3)
                   and (red["sh_coeffs"] == 11).all())
-        b = parallel.GradientBucket(n, C, "cpu")
-        b.data += rank + 1
-        b.sh += 10 ** rank
-        for p0, p1 in parallel.chunk_ranges(n, 3):
-            for w in b.all_reduce_chunk(p0, p1):
+        ranges = parallel.chunk_ranges(n, 3)
+        b = parallel.GradientBucket(n, C, "cpu", ranges=ranges)
+        for c in range(len(ranges)):
+            d_, a_, s_ = b.chunk_views(c)
+            d_ += rank + 1
+            s_ += 10 ** rank
+        for c in range(len(ranges)):
+            for w in b.all_reduce_chunk(c):
                 w.wait()
-        ok = ok and bool((b.data == 3).all() and (b.sh == 11).all() and (b.attr == 0).all())
+        data, attr, sh = b.gather()
+        ok = ok and bool((data == 3).all() and (sh == 11).all() and (attr == 0).all())
 
         class _S:   # image-tile sharding: every rank renders its row band, rank 0 assembles
             width, height = 6, 10

@@ -127,6 +127,7 @@ SIGNATURES = {
     "vp_get_stats": (C.c_int, [_VP, C.POINTER(vp_stats), _VP]),
     "vp_bounded_adam_step": (C.c_int, [C.c_int64, _VP, _VP, _VP, _VP, C.c_double, C.c_double, C.c_double, C.c_double,
                                        C.c_int, C.c_float, C.c_int, C.c_float, _VP]),
+    "vp_l1_loss_grad": (C.c_int, [C.c_int64, _VP, _VP, C.c_double, _VP, _VP, _VP]),
     "vp_debug_bvh": (C.c_int, [_VP, _VP, _VP, C.POINTER(C.c_int64), _VP]),
 }
 

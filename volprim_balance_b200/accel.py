@@ -17,7 +17,12 @@ from ._cabi import VolprimCudaError, vp_camera, vp_hit_record, vp_params, vp_ray
 
 
 def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else None
+    """Device address of a tensor -- or a raw address (int), for gradient rows that live inside a larger buffer."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t) if t else None
+    return C.c_void_p(t.data_ptr())
 
 
 def _f32(t: torch.Tensor, device) -> torch.Tensor:

@@ -64,7 +64,46 @@ __global__ void __launch_bounds__(256) k_bounded_adam(int64_t n, float *__restri
     }
 }
 
+// l1(reference, image) of volprim/optimizers.py:170-174 together with what dr.backward(loss) seeds the render op with
+// (d loss / d image = sign(image - reference) / n_total) and the squared error psnr() needs (:180-186): one pass, 8 B read
+// + 4 B written per element, block sums reduced into sums[0] (sum |diff| / n_total) and sums[1] (sum diff^2 / n_total).
+__global__ void __launch_bounds__(256) k_l1_loss_grad(int64_t n, const float *__restrict__ image, const float *__restrict__ reference,
+                                                      float inv_n_total, float *__restrict__ d_image, float *__restrict__ sums)
+{
+    float a = 0.f, q = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float diff = image[i] - __ldg(reference + i);
+        a += fabsf(diff);
+        q = fmaf(diff, diff, q);
+        d_image[i] = diff > 0.f ? inv_n_total : (diff < 0.f ? -inv_n_total : 0.f);
+    }
+    for (int off = 16; off; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        q += __shfl_xor_sync(0xffffffffu, q, off);
+    }
+    __shared__ float sa[8], sq[8];
+    if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sq[threadIdx.x >> 5] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ta = 0.f, tq = 0.f;
+        for (int k = 0; k < 8; ++k) { ta += sa[k]; tq += sq[k]; }
+        atomicAdd(sums, ta * inv_n_total);
+        atomicAdd(sums + 1, tq * inv_n_total);
+    }
+}
+
 }  // namespace
+
+extern "C" int vp_l1_loss_grad(int64_t n, const float *image, const float *reference, double n_total, float *d_image,
+                               float *sums, void *stream)
+{
+    if (n < 0 || !(n_total > 0) || (n > 0 && (!image || !reference || !d_image || !sums))) return VP_E_INVALID;
+    if (n == 0) return VP_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_l1_loss_grad<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, image, reference, (float)(1.0 / n_total), d_image, sums);
+    return cudaGetLastError() == cudaSuccess ? VP_OK : VP_E_CUDA;
+}
 
 extern "C" int vp_bounded_adam_step(int64_t n, float *param, const float *grad, float *m, float *v, double lr_t, double beta1,
                                     double beta2, double eps, int has_lower, float lower, int has_upper, float upper,

@@ -152,6 +152,28 @@ class BoundedAdam:
                    self.epsilon, self.bounds))
 
 
+def l1_loss_grad(reference, image, n_total=None, sums=None):
+    """Fused l1(reference, image) + its gradient w.r.t. `image` + the squared error psnr() needs (vp_l1_loss_grad, one
+    pass).  Returns (d_image, sums) with sums[0] = sum |diff| / n_total, sums[1] = sum diff^2 / n_total accumulated into
+    `sums` (so that the views of a batch film can be handled one at a time with n_total = the whole film's size)."""
+    import ctypes as C
+    from . import _cabi
+    image, reference = image.detach().contiguous(), reference.detach().contiguous()
+    if not image.is_cuda or image.dtype != torch.float32 or reference.shape != image.shape:
+        raise ValueError("l1_loss_grad: float32 CUDA tensors of equal shape")
+    n_total = float(n_total or image.numel())
+    if sums is None:
+        sums = torch.zeros(2, dtype=torch.float32, device=image.device)
+    d_image = torch.empty_like(image)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    with torch.cuda.device(image.device):
+        rc = _cabi.load_library().vp_l1_loss_grad(image.numel(), ptr(image), ptr(reference), n_total, ptr(d_image), ptr(sums),
+                                                  C.c_void_p(torch.cuda.current_stream(image.device).cuda_stream))
+    if rc != 0:
+        raise _cabi.VolprimCudaError(f"vp_l1_loss_grad failed ({rc})")
+    return d_image, sums
+
+
 def l1(reference, image):
     '''L1 loss function'''
     return (reference - image).abs().mean()

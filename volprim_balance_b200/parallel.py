@@ -69,43 +69,69 @@ def unpack_gradients(flat: torch.Tensor, like: Dict[str, torch.Tensor], keys: Se
 
 
 class GradientBucket:
-    """The primitive gradients of one rank as aligned views of ONE flat buffer: the adjoint kernels accumulate straight
-    into `data` [N*10], `attr` [N], `sh` [N*C]; the all-reduce runs over the flat buffer (no packing copy) or, chunk by
-    chunk, over the three slices of a primitive range while the next range is still being accumulated."""
+    """The primitive gradients of one rank in ONE flat buffer that the adjoint kernels accumulate into directly and the
+    all-reduce runs over -- no packing copy.
 
-    def __init__(self, n: int, sh_floats: int, device):
+    Layout: the primitives are cut into `ranges` ([p0, p1), boundaries on multiples of 4); range c owns one contiguous
+    slice [data rows p0..p1 | attr p0..p1 | sh rows p0..p1], every segment 16-byte aligned.  So the gradient of a range
+    is reduced with ONE collective call as soon as the primitive-major pass has finished that range, while the next range
+    is still being accumulated.  The kernels index their gradient arguments by the global primitive number; `pointers(c)`
+    returns base tensors shifted such that rows p0..p1 land in range c's slice (rows outside it are never touched by a
+    call restricted to that range).  With a single range the layout is the plain [data | attr | sh]."""
+
+    def __init__(self, n: int, sh_floats: int, device, ranges=None):
         self.n, self.sh_floats = n, sh_floats
-        sizes = (n * 10, n, n * sh_floats)
-        offs, off = [], 0
-        for sz in sizes:
-            offs.append(off)
-            off += _padded(sz)
-        self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=device)
-        self.data = self.flat[offs[0]:offs[0] + sizes[0]]
-        self.attr = self.flat[offs[1]:offs[1] + sizes[1]]
-        self.sh = self.flat[offs[2]:offs[2] + sizes[2]] if sh_floats else None
+        self.ranges = list(ranges) if ranges else [(0, n)]
+        per = 10 + 1 + sh_floats
+        self.flat = torch.zeros(max(sum(_padded((p1 - p0) * 10) + _padded(p1 - p0) + _padded((p1 - p0) * sh_floats)
+                                        for p0, p1 in self.ranges), 4), dtype=torch.float32, device=device)
+        self._seg, off = [], 0
+        for p0, p1 in self.ranges:
+            m = p1 - p0
+            d0 = off; off += _padded(m * 10)
+            a0 = off; off += _padded(m)
+            s0 = off; off += _padded(m * sh_floats)
+            self._seg.append((d0, a0, s0, off))
+        assert per >= 11
 
-    def tensors(self):
-        return self.data, self.attr, self.sh
+    def chunk_flat(self, c: int) -> torch.Tensor:
+        d0, _, _, end = self._seg[c]
+        return self.flat[d0:end]
+
+    def chunk_views(self, c: int):
+        """(data [m*10], attr [m], sh [m*C] | None) views of range c."""
+        (p0, p1), (d0, a0, s0, _) = self.ranges[c], self._seg[c]
+        m = p1 - p0
+        return (self.flat[d0:d0 + m * 10], self.flat[a0:a0 + m],
+                self.flat[s0:s0 + m * self.sh_floats] if self.sh_floats else None)
+
+    def pointers(self, c: int):
+        """Raw device addresses (g_data10, g_attr, g_sh) for a kernel call restricted to range c, shifted so that the
+        kernels' global primitive index p lands at row p - p0 of the range's slice."""
+        (p0, _), (d0, a0, s0, _) = self.ranges[c], self._seg[c]
+        base = self.flat.data_ptr()
+        return (base + 4 * (d0 - 10 * p0), base + 4 * (a0 - p0), base + 4 * (s0 - self.sh_floats * p0) if self.sh_floats else 0)
+
+    def gather(self):
+        """(data [N*10], attr [N], sh [N*C] | None) in the reference layouts (copies unless there is a single range)."""
+        parts = [self.chunk_views(c) for c in range(len(self.ranges))]
+        if len(parts) == 1:
+            return parts[0]
+        return (torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]),
+                torch.cat([p[2] for p in parts]) if self.sh_floats else None)
 
     def zero_(self):
         self.flat.zero_()
-
-    def chunk_views(self, p0: int, p1: int):
-        v = [self.data[10 * p0:10 * p1], self.attr[p0:p1]]
-        if self.sh is not None:
-            v.append(self.sh[self.sh_floats * p0:self.sh_floats * p1])
-        return v
 
     def all_reduce(self, group=None):
         if world()[1] > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
 
-    def all_reduce_chunk(self, p0: int, p1: int, group=None):
-        """Asynchronous SUM over the slices of primitives [p0, p1); returns the work handles."""
+    def all_reduce_chunk(self, c: int, group=None):
+        """Asynchronous SUM over the slice of range c (one collective); returns the work handle in a list."""
         if world()[1] == 1:
             return []
-        return [dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group, async_op=True) for v in self.chunk_views(p0, p1)]
+        return [dist.all_reduce(self.chunk_flat(c), op=dist.ReduceOp.SUM, group=group, async_op=True)]
 
 
 def chunk_ranges(n: int, n_chunks: int, granule: int = 4):

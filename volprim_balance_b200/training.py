@@ -19,14 +19,19 @@ import torch.distributed as dist
 
 from . import _cabi, parallel
 from .accel import RaySource
+from .optimizers import l1_loss_grad
 from .integrators.common import Ellipsoid
 
 
 class RefineStep:
-    def __init__(self, scene, sensors, targets, opt, n_chunks: int = 4, group=None, rebuild: str = 'rebuild'):
+    def __init__(self, scene, sensors, targets, opt, n_chunks: int = 4, group=None, rebuild: str = 'rebuild',
+                 rebuild_every: int = 8):
         """sensors: all views of the batch (PerspectiveSensor objects, identical film sizes); targets: {view index:
         [H, W, 3] CUDA tensor} for at least the views of this rank; opt: BoundedAdam holding 'centers', 'scales',
-        'quats', 'opacities', 'sh_coeffs' (the keys of refine_3dg_dataset.py:131-153)."""
+        'quats', 'opacities', 'sh_coeffs' (the keys of refine_3dg_dataset.py:131-153).  rebuild: 'rebuild' = a full LBVH
+        build after every step (what params.update() does in the reference), 'refit' = keep order and topology and
+        refresh the boxes, with a full build every `rebuild_every` steps (learning rates of 1e-4 barely move a
+        primitive between two steps)."""
         self.scene, self.integrator, self.shape = scene, scene.integrator, scene.ellipsoids()
         if self.integrator.integrator_id != _cabi.INTEGRATOR_RF:
             raise Exception("RefineStep drives the volprim_rf integrator")
@@ -35,10 +40,12 @@ class RefineStep:
         self.views = parallel.shard_views(len(self.sensors), self.rank, self.world)
         self.n_chunks = n_chunks
         self.shape.rebuild_policy = rebuild
+        self.rebuild_every, self._steps = max(1, int(rebuild_every)), 0
         n = self.shape.count
         shf = self.shape.attributes['sh_coeffs'].numel() // n if n else 0
-        self.bucket = parallel.GradientBucket(n, shf, self.shape.device)
         self.ranges = parallel.chunk_ranges(n, n_chunks)
+        self.bucket = parallel.GradientBucket(n, shf, self.shape.device, ranges=self.ranges)
+        self._sums = torch.zeros(2, dtype=torch.float32, device=self.shape.device)
         self.record = None
         self.timing = {}
         s0 = self.sensors[0]
@@ -53,6 +60,8 @@ class RefineStep:
         self.shape.attributes['opacities'] = o['opacities'].detach().reshape(-1).contiguous()
         self.shape.attributes['sh_coeffs'] = o['sh_coeffs'].detach().reshape(-1).contiguous()
         self.shape.parameters_changed()
+        if self.shape.rebuild_policy == 'refit' and self._steps % self.rebuild_every == 0:
+            self.shape._topology_n = -1          # periodic full build
         self.shape.bind('opacities', with_sh=True)
 
     def _ensure_record(self, acc, n_rays, id_cap):
@@ -79,11 +88,10 @@ class RefineStep:
         params = integ._vp_params(self.scene, None)
         id_cap = integ._cap()
         self.bucket.zero_()
-        outs = self.bucket.tensors()
-        loss = torch.zeros((), device=shape.device)
-        sq = torch.zeros((), device=shape.device)
+        self._sums.zero_()
         flags = torch.zeros(2, device=shape.device)      # records over capacity / rays cut at the per-ray cap
         works, images = [], {}
+        n_ranges = len(self.ranges)
         for k, vi in enumerate(self.views):
             s = self.sensors[vi]
             rays = RaySource(camera=s.vp_camera(), spp=1)
@@ -91,24 +99,21 @@ class RefineStep:
             res = acc.render_forward(params, rays, record=rec, id_cap=id_cap, want_beta=False, want_nhits=False)
             self._pinned_totals[k % self._pinned_totals.shape[0]].copy_(rec.total, non_blocking=True)
             flags += torch.stack([(rec.total[0] > rec.capacity).float(), (rec.total[1] > 0).float()])
-            img = res.rgb.reshape(s.height, s.width, 3)
-            diff = img - self.targets[vi]
-            loss += diff.abs().sum() / self.n_pix
-            sq += (diff * diff).sum() / self.n_pix
-            dL = torch.sign(diff).reshape(-1, 3) * (1.0 / self.n_pix)      # d l1(ref, image) / d image
+            # l1 over the batch film, its gradient and the squared error in one pass (optimizers.py:170-186)
+            dL, _ = l1_loss_grad(self.targets[vi], res.rgb.reshape(s.height, s.width, 3), n_total=self.n_pix, sums=self._sums)
             if want_images:
-                images[vi] = img
-            acc.adjoint_begin(params, rays, dL, res.rgb, rec, outs)
-            if k + 1 < len(self.views) or self.world == 1:
-                acc.adjoint_finish(params, rays, rec, 0, shape.count, outs)
-            else:
-                # last view of the rank: range by range, each range's all-reduce overlapping the next range's accumulation
-                for p0, p1 in self.ranges:
-                    acc.adjoint_finish(params, rays, rec, p0, p1, outs)
-                    works += self.bucket.all_reduce_chunk(p0, p1, self.group)
+                images[vi] = res.rgb.reshape(s.height, s.width, 3)
+            acc.adjoint_begin(params, rays, dL.reshape(-1, 3), res.rgb, rec, self.bucket.pointers(0))
+            last = k + 1 == len(self.views)
+            for c, (p0, p1) in enumerate(self.ranges):
+                acc.adjoint_finish(params, rays, rec, p0, p1, self.bucket.pointers(c))
+                if last and self.world > 1:
+                    # the all-reduce of range c runs on NCCL's stream while range c + 1 is still being accumulated
+                    works += self.bucket.all_reduce_chunk(c, self.group)
         if not self.views and self.world > 1:
-            for p0, p1 in self.ranges:
-                works += self.bucket.all_reduce_chunk(p0, p1, self.group)
+            for c in range(n_ranges):
+                works += self.bucket.all_reduce_chunk(c, self.group)
+        loss, sq = self._sums[0], self._sums[1]
         return self.bucket, works, ((loss, sq, images, flags) if want_images else (loss, sq, flags))
 
     def _step_once(self, want_images):
@@ -138,14 +143,16 @@ class RefineStep:
         if overflowed:
             return None                # redo the step with records sized from the new estimate
         # identical optimiser step on every rank (refine_3dg_dataset.py:178-189)
-        g = self.bucket.data.view(-1, 10)
+        g_data, g_attr, g_sh = self.bucket.gather()
+        g = g_data.view(-1, 10)
         o = self.opt
         o['centers'].grad = g[:, 0:3].contiguous()
         o['scales'].grad = g[:, 3:6].contiguous()
         o['quats'].grad = g[:, 6:10].contiguous()
-        o['opacities'].grad = self.bucket.attr.reshape(o['opacities'].shape).clone()
-        o['sh_coeffs'].grad = self.bucket.sh.reshape(o['sh_coeffs'].shape).clone()
+        o['opacities'].grad = g_attr.reshape(o['opacities'].shape).clone()
+        o['sh_coeffs'].grad = g_sh.reshape(o['sh_coeffs'].shape).clone()
         o.step()
+        self._steps += 1
         self.update_params()
         ev['end'].record()
         torch.cuda.current_stream().synchronize()
