@@ -26,6 +26,9 @@ from volprim_balance_b200.integrators.common import Ellipsoid  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--ply'); ap.add_argument('--cameras')
+ap.add_argument('--targets', help='.npy file [views, H, W, 3] with the target images of the --ply dataset (linear RGB)')
+ap.add_argument('--fused_step', action='store_true', help='drive the kernels through volprim.training.RefineStep: gradient all-reduce '
+                'cut into primitive ranges and overlapped with the last view\'s accumulation (same gradients as loss.backward())')
 ap.add_argument('--primitives', type=int, default=200_000)
 ap.add_argument('--cam_count', type=int, default=8)
 ap.add_argument('--width', type=int, default=640); ap.add_argument('--height', type=int, default=360)
@@ -82,7 +85,10 @@ if target_prim is not None:
     refs = {i: volprim.render(ref_scene, sensor=sensor_objs[i], spp=1, jitter=False) for i in mine}
     del ref_scene
 else:
-    raise SystemExit('reference images for --ply datasets are loaded by the caller (no image reader on the hot path)')
+    if not args.targets:
+        raise SystemExit('--ply needs --targets FILE.npy ([views, H, W, 3], the images of the selected cameras)')
+    stack = np.load(args.targets)
+    refs = {i: torch.from_numpy(np.ascontiguousarray(stack[i], dtype=np.float32)).cuda() for i in mine}
 if args.refit:
     scene.ellipsoids().rebuild_policy = 'refit'
 
@@ -108,6 +114,17 @@ def update_params():
 
 update_params()
 n_pix = len(sensor_objs) * sensor_objs[0].width * sensor_objs[0].height * 3
+if args.fused_step:
+    from volprim_balance_b200 import training
+    step = training.RefineStep(scene, sensor_objs, refs, opt, rebuild='refit' if args.refit else 'rebuild')
+    for it in range(args.iterations):
+        t0 = time.time()
+        loss, sq = step.step()
+        if rank == 0:
+            psnr = 10 * np.log10(1.0 / max(float(sq), 1e-20))
+            print(f'-- step {it + 1} / {args.iterations} | psnr={psnr:.04f} | loss={float(loss):.06f} | '
+                  f'{1e3 * (time.time() - t0):.1f} ms (exposed all-reduce {step.timing["exposed_allreduce_ms"]:.2f} ms)', flush=True)
+    args.iterations = 0
 for it in range(args.iterations):
     t0 = time.time()
     opt.zero_grad()

@@ -261,8 +261,8 @@ class EllipsoidAccel:
             dense = with_state is not False and self.sh_floats > 0 and id_cap * n_rays * 24 <= self.dense_budget_bytes
         if dense:
             return HitRecord(n_rays, self.n, capacity, id_cap, self.device, dense=True)
-        if with_state is None:
-            with_state = capacity * 16 <= self.state_budget_bytes
+        if with_state is None:      # (only volprim_rf hits carry a colour; tomography records are the id lists)
+            with_state = self.sh_floats > 0 and capacity * 16 <= self.state_budget_bytes
         return HitRecord(n_rays, self.n, capacity, id_cap, self.device, with_state=with_state)
 
     def record_bytes(self, n_rays: int, id_cap: int) -> int:

@@ -272,111 +272,114 @@ def scale_films(d: dict, scale: float = 1.0) -> dict:
     return d
 
 
+_ASSET_HEADER = ('import os', 'from os.path import join, dirname', 'import numpy as np', 'import drjit as dr',
+                 'import mitsuba as mi', 'from mitsuba.scalar_rgb import ScalarTransform4f as T')
+_ASSET_SENSORS = ('perspective', 'orthographic', 'thinlens')
+_ASSET_EMITTERS = ('envmap', 'constant', 'point', 'distant', 'spot', 'directional')
+_ASSET_SUBFOLDER = {'.json': 'data', '.obj': 'meshes', '.jpg': 'textures', '.png': 'textures', '.exr': 'textures'}
+_ASSET_FOREIGN = ('meshholder', 'obj', 'ply', 'bitmap', 'envmap')      # scene content outside the volprim hot path
+
+
+class _AssetWriter:
+    """Emits the text of an asset's `__init__.py` (the file format of reference io.py:87-272: three dictionaries
+    OBJECTS / SENSORS / EMITTERS written as Python literals, arrays and primitive clouds moved to files next to it).
+    One `emit_*` method per kind of value; `emit` dispatches on the value."""
+
+    def __init__(self, folder: str):
+        self.folder = folder
+
+    # -- files that travel with the asset ----------------------------------------------------------------
+    def _subdir(self, name: str) -> str:
+        os.makedirs(join(self.folder, name), exist_ok=True)
+        return name
+
+    def store_ellipsoids(self, node: dict, path: str) -> dict:
+        """Tensor-defined ellipsoids shape -> data/<path>.ply; returns the node with a `filename` instead of arrays."""
+        is_array = lambda v: isinstance(v, np.ndarray) or hasattr(v, 'detach')
+        geometry = ('centers', 'scales', 'quaternions')
+        attributes = [k for k, v in node.items() if is_array(v) and k not in geometry]
+        target = join(self.folder, self._subdir('data'), f'{path}.ply')
+        ellipsoid_dict_to_ply(node, attributes, target)
+        slim = {k: v for k, v in node.items() if k not in geometry and k not in attributes}
+        slim['filename'] = target
+        return slim
+
+    def store_array(self, value, path: str, key: str) -> str:
+        rel = f"{self._subdir('data')}/{path}.{key}.npy"
+        np.save(join(self.folder, rel), np.asarray(value.detach().cpu() if hasattr(value, 'detach') else value))
+        return rel
+
+    def store_file(self, src: str, ellipsoids: bool) -> str:
+        stem, ext = splitext(basename(src))
+        sub = 'data' if (ext == '.ply' and ellipsoids) else ('meshes' if ext == '.ply' else _ASSET_SUBFOLDER[ext])
+        rel = join(self._subdir(sub), stem + ext)
+        if not exists(join(self.folder, rel)):
+            shutil.copy(src, join(self.folder, rel))
+        return rel
+
+    # -- literals --------------------------------------------------------------------------------------
+    @staticmethod
+    def emit_transform(value, pad: str, as_look_at: bool) -> str:
+        T = Transform4f(value)
+        if as_look_at:      # sensors are written as look_at(origin, target, up), like the reference does
+            origin, target = T @ np.zeros(3), T @ np.array([0.0, 0.0, 1.0])
+            up = T.transform_vector([0.0, 1.0, 0.0])
+            rows = [f"origin={origin.tolist()}", f"target={target.tolist()}", f"up={up.tolist()}"]
+            return "T().look_at(\n" + ''.join(f"{pad}         {r},\n" for r in rows) + f"{pad}     )"
+        m = T.matrix.tolist()
+        return f"T([{m[0]}, {m[1]}, {m[2]}, {m[3]}])"
+
+    def emit(self, key: str, value, node_type, ellipsoids: bool, path: str, pad: str, depth: int) -> str:
+        if isinstance(value, dict):
+            return self.emit_dict(value, f'{path}.{key}', depth + 1)
+        if isinstance(value, str):
+            if key == 'filename':
+                return "r'" + self.store_file(value, ellipsoids) + "'"
+            return "'" + (value.replace('.', '_') if key == 'id' else value) + "'"
+        if key == 'to_world' or isinstance(value, Transform4f):
+            return self.emit_transform(value, pad, as_look_at=key == 'to_world' and node_type in _ASSET_SENSORS)
+        if isinstance(value, np.ndarray) or hasattr(value, 'detach'):
+            return f"np.load(join(dirname(__file__), '{self.store_array(value, path, key)}'))"
+        return str(value)
+
+    def emit_dict(self, node: dict, path: str, depth: int = 0, with_resources: bool = False) -> str:
+        pad = ' ' * (4 * depth)
+        node_type = node.get('type')
+        if node_type in _ASSET_FOREIGN:
+            raise Exception(f"dict_to_asset: '{node_type}' objects are outside the volprim hot path")
+        ellipsoids = isinstance(node_type, str) and 'ellipsoid' in node_type
+        if ellipsoids and 'filename' not in node:
+            node = self.store_ellipsoids(dict(node), path)
+        lines = []
+        if with_resources:
+            lines.append("'resources': { 'type': 'resources', 'path': dirname(__file__) }")
+        for key, value in node.items():
+            if isinstance(value, dict) and value.get('type') == 'resources':
+                continue
+            lines.append(f"'{key.replace('.', '_')}': " + self.emit(key, value, node_type, ellipsoids, path, pad, depth))
+        text = '{\n' + ''.join(f"{pad}    {line},\n" for line in lines) + pad + '}'
+        return text.replace('\\', '/')
+
+
 def dict_to_asset(scene_dict: dict, output_folder: str, verbose=False):
     '''
-    Generate a Python asset that contains a dictionary that represents a scene (reference io.py:87-272):
-    `__init__.py` with OBJECTS / SENSORS / EMITTERS, ellipsoid shapes in data/<path>.ply, arrays in
+    Generate a Python asset that contains a dictionary that represents a scene (file format of reference
+    io.py:87-272): `__init__.py` with OBJECTS / SENSORS / EMITTERS, ellipsoid shapes in data/<path>.ply, arrays in
     data/<path>.<key>.npy.  The header imports are the reference's, so the asset also loads under Mitsuba.
     '''
-    sensor_types = ['perspective', 'orthographic', 'thinlens']
-    emitter_types = ['envmap', 'constant', 'point', 'distant', 'spot', 'directional']
-    print(f'Writing asset to {output_folder} ...')
-
-    def dict_to_string(d, path, indent=0, add_resources=False) -> str:
-        w = lambda x: ' ' * indent + x
-        sanitize = lambda x: x.replace('.', '_')
-        d = dict(d)
-        object_type = d.get('type', None)
-        s = '{\n'
-        if add_resources:
-            s += w("    'resources': { 'type': 'resources', 'path': dirname(__file__) },\n")
-        if object_type in ('meshholder', 'obj', 'ply', 'bitmap', 'envmap'):
-            raise Exception(f"dict_to_asset: '{object_type}' objects are outside the volprim hot path")
-        is_ellipsoid = bool(object_type) and 'ellipsoid' in object_type
-        if is_ellipsoid and 'filename' not in d:
-            is_arr = lambda v: isinstance(v, np.ndarray) or hasattr(v, 'detach')
-            extras_keys = [k for k in d if is_arr(d[k]) and k not in ('centers', 'scales', 'quaternions')]
-            os.makedirs(join(output_folder, 'data'), exist_ok=True)
-            filename = join(output_folder, 'data', f'{path}.ply')
-            ellipsoid_dict_to_ply(d, extras_keys, filename)
-            for k in extras_keys + ['centers', 'scales', 'quaternions']:
-                del d[k]
-            d['filename'] = filename
-        for k, v in d.items():
-            if isinstance(v, dict) and v.get('type') == 'resources':
-                continue
-            s += w(f"    '{sanitize(k)}': ")
-            if isinstance(v, dict):
-                s += dict_to_string(v, f'{path}.{k}', indent + 4) + ",\n"
-            elif isinstance(v, str):
-                if k == 'filename':
-                    src = v
-                    base, ext = splitext(basename(src))
-                    dst_folder = {'.ply': 'data' if is_ellipsoid else 'meshes', '.json': 'data', '.obj': 'meshes',
-                                  '.jpg': 'textures', '.png': 'textures', '.exr': 'textures'}[ext]
-                    os.makedirs(join(output_folder, dst_folder), exist_ok=True)
-                    v = join(dst_folder, f'{base}{ext}')
-                    dst = join(output_folder, v)
-                    if not exists(dst):
-                        shutil.copy(src, dst)
-                    s += f"r'{v}',\n"
-                else:
-                    if k == 'id':
-                        v = sanitize(v)
-                    s += f"'{v}',\n"
-            elif k == 'to_world':
-                T = Transform4f(v)
-                if object_type in sensor_types:
-                    origin, target = T @ np.zeros(3), T @ np.array([0.0, 0.0, 1.0])
-                    up = T.transform_vector([0.0, 1.0, 0.0])
-                    s += "T().look_at(\n"
-                    s += w(f"         origin={origin.tolist()},\n")
-                    s += w(f"         target={target.tolist()},\n")
-                    s += w(f"         up={up.tolist()},\n")
-                    s += w("     ),\n")
-                else:
-                    m = T.matrix.tolist()
-                    s += f"T([{m[0]}, {m[1]}, {m[2]}, {m[3]}]),\n"
-            elif isinstance(v, np.ndarray) or hasattr(v, 'detach'):
-                os.makedirs(join(output_folder, 'data'), exist_ok=True)
-                filename = f'data/{path}.{k}.npy'
-                np.save(join(output_folder, filename), np.asarray(v.detach().cpu() if hasattr(v, 'detach') else v))
-                s += f"np.load(join(dirname(__file__), '{filename}')),\n"
-            elif isinstance(v, Transform4f):
-                m = v.matrix.tolist()
-                s += "T([\n" + ''.join(w(f"         {row},\n") for row in m) + w("     ]),\n")
-            else:
-                s += f"{v},\n"
-        s += w('}')
-        return s.replace('\\', '/')
-
     assert scene_dict['type'] == 'scene', 'can only process scene dictionary!'
-    sensors, emitters, objects = {}, {}, {}
-    for k, v in scene_dict.items():
-        if isinstance(v, str) and v == 'scene':
+    print(f'Writing asset to {output_folder} ...')
+    groups = {'OBJECTS': {}, 'SENSORS': {}, 'EMITTERS': {}}
+    for key, value in scene_dict.items():
+        if key == 'type':
             continue
-        if v['type'] in sensor_types:
-            sensors[k] = v
-        elif v['type'] in emitter_types:
-            emitters[k] = v
-        else:
-            objects[k] = v
-
+        kind = value['type']
+        groups['SENSORS' if kind in _ASSET_SENSORS else 'EMITTERS' if kind in _ASSET_EMITTERS else 'OBJECTS'][key] = value
     os.makedirs(output_folder, exist_ok=True)
+    writer = _AssetWriter(output_folder)
+    blocks = [f'{title} = ' + writer.emit_dict(group, 'root', with_resources=True) for title, group in groups.items()]
     with open(join(output_folder, '__init__.py'), 'w') as f:
-        f.write('import os\n')
-        f.write('from os.path import join, dirname\n')
-        f.write('import numpy as np\n')
-        f.write('import drjit as dr\n')
-        f.write('import mitsuba as mi\n')
-        f.write('from mitsuba.scalar_rgb import ScalarTransform4f as T\n')
-        f.write('\n')
-        for title, group in (('OBJECTS', objects), ('SENSORS', sensors), ('EMITTERS', emitters)):
-            f.write(f'{title} = ')
-            f.write(dict_to_string(group, 'root', add_resources=True))
-            f.write('\n')
-            if title != 'EMITTERS':
-                f.write('\n')
+        f.write('\n'.join(_ASSET_HEADER) + '\n\n' + '\n\n'.join(blocks) + '\n')
 
 
 def object_to_dict(root) -> dict:
