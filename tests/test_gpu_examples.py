@@ -26,8 +26,9 @@ def test_optimize_volume_fits_and_writes_a_loadable_asset(tmp_path):
     assert len(psnr) == 12 and psnr[-1] > psnr[0], psnr
     assert os.path.exists(os.path.join(out, "optimized_asset", "__init__.py"))
     text = _run(["examples/render_asset.py", "--asset", os.path.join(out, "optimized_asset"), "--output", str(tmp_path / "r"), "--spp", "2"])
-    assert "cam_0000" in text and os.path.exists(str(tmp_path / "r" / "cam_0000.npy"))
-    assert np.load(str(tmp_path / "r" / "cam_0000.npy")).shape == (64, 64, 3)
+    names = [l.split(":")[0] for l in text.splitlines() if "(64, 64, 3)" in l]
+    assert len(names) == 3 and all(os.path.exists(str(tmp_path / "r" / f"{n}.npy")) for n in names), text
+    assert np.load(str(tmp_path / "r" / f"{names[0]}.npy")).shape == (64, 64, 3)
 
 
 @pytest.mark.parametrize("fused", [False, True], ids=["autograd", "fused_step"])
