@@ -66,17 +66,20 @@ def report(rep, title, how):
 
 HOW = ("Captured with `ncu --section SourceCounters --section WarpStateStats --section SchedulerStats --section Occupancy --section "
        "LaunchStats --section MemoryWorkloadAnalysis --section SpeedOfLight --metrics dram__bytes_read.sum,dram__bytes_write.sum,"
-       "gpu__time_duration.sum,lts__t_sectors_op_red.sum,lts__t_sectors_op_atom.sum --clock-control none --import-source on` on "
+       "gpu__time_duration.sum,lts__t_sectors_op_red.sum,lts__t_sectors_op_atom.sum --clock-control none` on "
        "`python scripts/ab.py cfg2` (workload = bench.py's cfg2), after the same command had exited 0 without ncu.  (The section list "
        "replaces `--set full`: a full-set capture replays the 1.4 GB working set of these kernels ~40 times.)")
-t = report(fwd_rep, "Top kernel: k_trace_forward, one launch", HOW)
-fwd_traffic = next((v for k, v in t.items() if "k_trace_forward" in k), None)
-report(adj_rep, "Recording forward + the adjoint passes, one launch each", HOW)
+t = report(fwd_rep, "k_trace_forward (plain, then recording) and the adjoint passes, one launch each" if fwd_rep == adj_rep
+           else "Top kernel: k_trace_forward, one launch", HOW)
+fwd_traffic = next((v for k, v in t.items() if "k_trace_forward" in k), None)   # first match = the plain (bench) instantiation
+if adj_rep != fwd_rep:
+    report(adj_rep, "Recording forward + the adjoint passes, one launch each", HOW)
 if fwd_traffic is not None:
     json.dump({"k_trace_forward_dram_bytes_per_launch": fwd_traffic, "source": os.path.basename(fwd_rep),
                "source_stamp": bench.source_stamp()}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"))
-reg = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_regions.py"), fwd_rep], capture_output=True, text=True).stdout
-out.append("\n## k_trace_forward: warp-stall samples per device function (source-correlated, -lineinfo)\n\n```\n" + reg + "```")
+for kern in ["k_trace_forward", "k_adjoint_rows_dense", "k_adjoint_gather"]:
+    reg = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_regions.py"), fwd_rep, kern], capture_output=True, text=True).stdout
+    out.append(f"\n## {kern}: warp-stall samples per device function (source-correlated, -lineinfo)\n\n```\n" + reg + "```")
 if bench_json and os.path.exists(bench_json):
     out.append("\n## Bench line of the same build (no profiler attached)\n\n```json\n" + open(bench_json).read().strip().splitlines()[-1] + "\n```")
 open(os.path.join(ROOT, "profiles", f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")

@@ -1,17 +1,20 @@
 """Aggregate ncu stall samples / instructions per device function of vp_trace.cu (by source line ranges)."""
 import csv, re, subprocess, sys
 rep = sys.argv[1]
+kern = sys.argv[2] if len(sys.argv) > 2 else None      # optional: only this kernel (regex), first launch in the report
 src = open('/root/repo/volprim_balance_b200/csrc/vp_trace.cu').read().split('\n')
 marks = []
 for i, l in enumerate(src, 1):
-    m = re.match(r'^(?:__device__ __forceinline__|__global__|template <.*>\s*$)?.*?\b(exact_isect|fast_isect|slab|list_insert_key|list_insert|drain_list|walk_ray|tile_capsule|tile_prism|prism_may_hit|capsule_children|walk_tile|sh_basis|sh_color|rf_eval|gauss_density_integral|epan_density_integral|srgb_to_linear|ray_index|flush_counters|k_trace_forward|rf_adjoint_hit|tomo_adjoint_hit|k_trace_adjoint|k_raygen)\(', l)
-    if m and (l.startswith('__device__') or l.startswith('__global__')): marks.append((i, m.group(1)))
+    if l.startswith('__device__') or l.startswith('__global__'):
+        m = re.search(r'\b(\w+)\(', re.sub(r'__launch_bounds__\([^)]*\)', '', l))
+        if m: marks.append((i, m.group(1)))
 def fn(line):
     name = 'header'
     for i, n in marks:
         if line >= i - 3: name = n
     return name
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+flt = ["-k", "regex:" + kern, "-c", "1"] if kern else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"] + flt, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur, hdr, R = None, None, {}
 for r in rows:
