@@ -61,6 +61,17 @@ VIEWS_PER_STEP = 24        # one step = this many views (a >= 2 s timed region a
 TRAIN_VIEWS = 8            # fixed global batch of the training step (BASELINE configs[3]: 8 views / step)
 RAY_IO_BYTES = 44          # 28 B read (o, d, maxt) + 16 B written (rgb, T)        BASELINE.md section 5
 EVAL_BYTES_SH3 = 236       # 40 geometry + 4 opacity + 192 SH per primitive evaluation
+# gather-formulation adjoint: per recorded hit 4 B id read + 4 B rank written (counting pass), 20 B record
+# (id + colour/transmittance state) + 4 B rank read + 32 B bucket entry written (ray pass), 32 B entry read (primitive pass);
+# per primitive 236 B parameters read + 59 gradient floats read-modify-written; per ray 12 B image gradient + 4 B hit count
+ADJ_HIT_BYTES = 96
+ADJ_PRIM_BYTES_SH3 = 236 + 2 * 59 * 4
+ADJ_RAY_BYTES = 16
+REC_HIT_BYTES = 20         # what the recording forward adds per hit (id + state)
+
+
+def adjoint_bytes(rays, hits, prims):
+    return rays * ADJ_RAY_BYTES + hits * ADJ_HIT_BYTES + prims * ADJ_PRIM_BYTES_SH3
 
 
 def measured_peak():
@@ -483,6 +494,29 @@ def run_ours(args, wl, rank, world, local_rank):
     import ctypes
     cam_bytes = ctypes.sizeof(vp._cabi.vp_camera)
 
+    # ---- ONE view cut into row strips over the ranks, image gathered on rank 0 (strong scaling of a single view) ---
+    tiles = None
+    if not args.no_extras or world > 1:
+        spr = 4 if world > 1 else 1
+        one = lambda v: parallel.render_tiles(scene, sensors[v % V], vp.render, spp=1, jitter=False, strips_per_rank=spr)
+        for v in range(3):
+            one(v)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_tv = 16
+        t0.record()
+        for v in range(n_tv):
+            one(v)
+        t1.record()
+        barrier()
+        tms = torch.tensor([t0.elapsed_time(t1) / n_tv], device=dev)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        tiles = {"what": f"one {W}x{H} view at a time through parallel.render_tiles(scene, sensor, render): {spr} interleaved "
+                         f"row strip(s) per rank over {world} GPU(s), strips gathered into the image on rank 0 (NCCL gather)",
+                 "scaling": "strong", "ms_per_view": float(tms.item()), "Mrays_per_s": R / float(tms.item()) / 1e3,
+                 "strips_per_rank": spr}
+
     # ---- training step on a FIXED batch of TRAIN_VIEWS views, sharded over the ranks (strong scaling) --------------
     train = None
     if not args.no_train and wl.get("kernel", "gaussian") == "gaussian" and wl["n"] <= 3_000_000:
@@ -523,7 +557,7 @@ def run_ours(args, wl, rank, world, local_rank):
         north = {"workload": wl3["desc"], "primitives": wl3["n"], "hits_per_ray": h3 / 8 / R3,
                  "forward_ms_per_view": fwd3, "forward_Mrays_per_s": R3 / fwd3 / 1e3,
                  "forward_roofline_frac": bytes3 / (fwd3 * 1e-3) / 1e9 / peak, **fa3,
-                 "fwd_adjoint_algorithmic_GBps": (bytes3 + R3 * (RAY_IO_BYTES + 24) + h3 / 8 * 3 * EVAL_BYTES_SH3)
+                 "fwd_adjoint_algorithmic_GBps": (bytes3 + h3 / 8 * REC_HIT_BYTES + adjoint_bytes(R3, h3 / 8, wl3["n"]))
                  / (fa3["fwd_adjoint_ms_per_view"] * 1e-3) / 1e9}
         north["fwd_adjoint_roofline_frac"] = north["fwd_adjoint_algorithmic_GBps"] / peak
         del scene3, sh3, acc3, cloud3
@@ -543,7 +577,7 @@ def run_ours(args, wl, rank, world, local_rank):
                "sample": f"CPU restatement of the reference loop (oracle/volprim_oracle.c, OpenMP, one BVH closest-hit query per "
                          f"hit) on {what}: {n} rays, mean hits/ray {h:.1f}, {dt:.2f} s"}
     adj_ms = fa["adjoint_ray_pass_ms"] + fa["adjoint_primitive_pass_ms"]
-    adj_bytes = R * (RAY_IO_BYTES + 24) + fa["hits_last_view"] * 3 * EVAL_BYTES_SH3
+    adj_bytes = adjoint_bytes(R, fa["hits_last_view"], wl["n"])
     line = {
         "metric": "volprim_rf forward Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -565,8 +599,10 @@ def run_ours(args, wl, rank, world, local_rank):
                      "kernel_ms": sum(kern_ms) / len(kern_ms), "peak_source": peak_src, "source_stamp": source_stamp()},
         "primitive_evals_per_s": mean_hits * R * n_launch * world / (total_ms * 1e-3),
         "fwd_adjoint_ms_per_view": fa["fwd_adjoint_ms_per_view"],
-        "adjoint": {"formulation": "gather: ray-major replay into per-primitive buckets (k_trace_adjoint<bucket>) + one warp per "
-                                   "primitive (k_adjoint_gather), no global reductions", **fa,
+        "adjoint": {"formulation": "gather: counting pass over the hit record (k_bucket_ranks_dense), ray-major replay into "
+                                   "per-primitive buckets (k_adjoint_rows_dense), one warp per primitive (k_adjoint_gather); no "
+                                   "global float reductions", **fa,
+                    "byte_model": f"{ADJ_HIT_BYTES} B/recorded hit + {ADJ_PRIM_BYTES_SH3} B/primitive + {ADJ_RAY_BYTES} B/ray",
                     "kernel_ms": adj_ms, "algorithmic_bytes_per_launch": adj_bytes,
                     "achieved": adj_bytes / (adj_ms * 1e-3) / 1e9, "unit": "GB/s",
                     "frac": adj_bytes / (adj_ms * 1e-3) / 1e9 / peak,
@@ -582,6 +618,8 @@ def run_ours(args, wl, rank, world, local_rank):
                 line["roofline"]["traffic_source"] = t.get("source")
         except Exception:
             pass
+    if tiles:
+        line["single_view_tiles"] = tiles
     if train:
         line["train_step"] = train
     if north:

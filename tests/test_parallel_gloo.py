@@ -21,6 +21,12 @@ def test_shards_partition_views_and_rows():
         assert bands[0][0] == 0 and bands[-1][1] == h
         assert all(bands[i][1] == bands[i + 1][0] for i in range(ws - 1))
         assert all(b[0] % 4 == 0 for b in bands if b[1] > b[0])
+    for h, ws, k in ((1080, 8, 4), (1080, 3, 5), (6, 4, 2), (50, 2, 1)):     # interleaved strips tile the rows exactly once
+        strips = sorted(b for r in range(ws) for b in parallel.shard_row_strips(h, r, ws, k))
+        assert strips[0][0] == 0 and strips[-1][1] == h
+        assert all(a[1] == b[0] for a, b in zip(strips, strips[1:]))
+        rows = [sum(b - a for a, b in parallel.shard_row_strips(h, r, ws, k)) for r in range(ws)]
+        assert max(rows) - min(rows) <= 4 * k + 4
 
 
 def test_packed_gradient_segments_are_aligned_and_ranges_tile():
@@ -88,6 +94,14 @@ def _worker(rank, ws, port, q):
         tiled = parallel.render_tiles(None, _S, band_of)
         if rank == 0:
             ok = ok and tiled.shape == (10, 6, 3) and torch.equal(tiled[:, 0, 0], torch.arange(10.0))
+        else:
+            ok = ok and tiled is None
+
+        class _S2:
+            width, height = 6, 50
+        tiled = parallel.render_tiles(None, _S2, band_of, strips_per_rank=3)        # interleaved strips
+        if rank == 0:
+            ok = ok and tiled.shape == (50, 6, 3) and torch.equal(tiled[:, 0, 0], torch.arange(50.0))
         else:
             ok = ok and tiled is None
         n_views = 5

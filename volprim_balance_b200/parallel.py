@@ -42,6 +42,21 @@ def shard_rows(height: int, rank: int = None, world_size: int = None, granule: i
     return min(s0 * granule, height), min(s1 * granule, height)
 
 
+def shard_row_strips(height: int, rank: int = None, world_size: int = None, strips_per_rank: int = 1, granule: int = 4):
+    """Row bands [(y0, y1), ...] of one image for `rank` when the image is cut into `strips_per_rank * world_size` strips
+    dealt round-robin (strip j belongs to rank j % world_size): interleaving evens out the load when the primitives
+    cover only part of the film.  `strips_per_rank=1` is `shard_rows`."""
+    if rank is None:
+        rank, world_size = world()
+    n = max(1, strips_per_rank) * world_size
+    out = []
+    for j in range(rank, n, world_size):
+        y0, y1 = shard_rows(height, j, n, granule)
+        if y1 > y0:
+            out.append((y0, y1))
+    return out
+
+
 def _padded(n: int, granule: int = 4) -> int:
     return (n + granule - 1) // granule * granule
 
@@ -134,14 +149,26 @@ class GradientBucket:
         return [dist.all_reduce(self.chunk_flat(c), op=dist.ReduceOp.SUM, group=group, async_op=True)]
 
 
-def chunk_ranges(n: int, n_chunks: int, granule: int = 4):
-    """[p0, p1) primitive ranges of about equal size with boundaries on multiples of `granule` (aligned slices)."""
+def chunk_ranges(n: int, n_chunks: int, granule: int = 4, taper: bool = False):
+    """[p0, p1) primitive ranges with boundaries on multiples of `granule` (aligned slices): about equal sizes, or with
+    `taper` sizes falling like n_chunks : ... : 2 : 1 -- the all-reduce of the LAST range cannot overlap anything, so it
+    should be the smallest."""
     n_chunks = max(1, min(n_chunks, max(1, n // granule)))
-    step = _padded((n + n_chunks - 1) // n_chunks, granule)
-    out, p = [], 0
-    while p < n:
-        out.append((p, min(n, p + step)))
-        p += step
+    if not taper:
+        step = _padded((n + n_chunks - 1) // n_chunks, granule)
+        out, p = [], 0
+        while p < n:
+            out.append((p, min(n, p + step)))
+            p += step
+        return out
+    total = n_chunks * (n_chunks + 1) // 2
+    out, p, acc = [], 0, 0
+    for c in range(n_chunks):
+        acc += n_chunks - c
+        q = n if c + 1 == n_chunks else min(n, _padded(n * acc // total, granule))
+        if q > p:
+            out.append((p, q))
+        p = q
     return out
 
 
@@ -187,29 +214,37 @@ def gather_images(local: Dict[int, torch.Tensor], n_views: int, dst: int = 0, gr
     return out
 
 
-def render_tiles(scene, sensor, render_fn, dst: int = 0, group=None, **kw):
-    """ONE view over all ranks (views < GPUs): every rank renders its band of 4-row tile strips with
-    `render_fn(scene, sensor=sensor, rows=(y0, y1), **kw)`; the bands are gathered on rank `dst` (NCCL gather over
-    NVLink when the process group is NCCL), which returns the assembled [H, W, 3] image; None elsewhere."""
+def render_tiles(scene, sensor, render_fn, dst: int = 0, group=None, strips_per_rank: int = 1, **kw):
+    """ONE view over all ranks (views < GPUs): every rank renders its 4-row-granular strips (`shard_row_strips`;
+    `strips_per_rank` > 1 interleaves them for load balance) with `render_fn(scene, sensor=sensor, rows=(y0, y1), **kw)`;
+    the strips are gathered on rank `dst` (ONE NCCL gather over NVLink when the process group is NCCL), which returns
+    the assembled [H, W, 3] image; None elsewhere."""
     rank, ws = world()
-    H = sensor.height
-    y0, y1 = shard_rows(H, rank, ws)
-    band = render_fn(scene, sensor=sensor, rows=(y0, y1), **kw) if y1 > y0 else None
+    H, W = sensor.height, sensor.width
+    mine = shard_row_strips(H, rank, ws, strips_per_rank)
+    parts = [render_fn(scene, sensor=sensor, rows=b, **kw) for b in mine]
     if ws == 1:
-        return band
-    W = sensor.width
-    bands = [shard_rows(H, r, ws) for r in range(ws)]
-    max_rows = max(b - a for a, b in bands)
-    device = band.device if band is not None else (torch.device('cuda', torch.cuda.current_device())
-                                                   if dist.get_backend(group) == 'nccl' else torch.device('cpu'))
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+    layout = [shard_row_strips(H, r, ws, strips_per_rank) for r in range(ws)]
+    max_rows = max(sum(b - a for a, b in bands) for bands in layout)
+    device = parts[0].device if parts else (torch.device('cuda', torch.cuda.current_device())
+                                            if dist.get_backend(group) == 'nccl' else torch.device('cpu'))
     buf = torch.zeros((max_rows, W, 3), dtype=torch.float32, device=device)
-    if band is not None:
-        buf[:y1 - y0] = band
+    at = 0
+    for (a, b), part in zip(mine, parts):
+        buf[at:at + b - a] = part
+        at += b - a
     bufs = [torch.empty_like(buf) for _ in range(ws)] if rank == dst else None
     dist.gather(buf, bufs, dst=dst, group=group)
     if rank != dst:
         return None
-    return torch.cat([bufs[r][:b - a] for r, (a, b) in enumerate(bands) if b > a], dim=0)
+    image = torch.empty((H, W, 3), dtype=torch.float32, device=device)
+    for r, bands in enumerate(layout):
+        at = 0
+        for a, b in bands:
+            image[a:b] = bufs[r][at:at + b - a]
+            at += b - a
+    return image
 
 
 def render_views(scene, sensors: Sequence, render_fn, dst: int = 0, **kw):

@@ -43,7 +43,8 @@ class RefineStep:
         self.rebuild_every, self._steps = max(1, int(rebuild_every)), 0
         n = self.shape.count
         shf = self.shape.attributes['sh_coeffs'].numel() // n if n else 0
-        self.ranges = parallel.chunk_ranges(n, n_chunks)
+        # several ranks: tapered ranges, the last (whose all-reduce is exposed) the smallest; one rank: nothing to overlap
+        self.ranges = parallel.chunk_ranges(n, n_chunks if self.world > 1 else 1, taper=True)
         self.bucket = parallel.GradientBucket(n, shf, self.shape.device, ranges=self.ranges)
         self._sums = torch.zeros(2, dtype=torch.float32, device=self.shape.device)
         self.record = None
@@ -51,6 +52,12 @@ class RefineStep:
         s0 = self.sensors[0]
         self.n_pix = len(self.sensors) * s0.width * s0.height * 3
         self._pinned_totals = torch.zeros((max(len(self.sensors), 1), 2), dtype=torch.int64).pin_memory()
+        # records over capacity / rays cut at the per-ray cap, over all views and ranks: known once the LAST primal pass
+        # is done, i.e. long before the adjoint of that view is -- the host takes the redo decision while the GPU works
+        self._flags = torch.zeros(2, dtype=torch.float32, device=self.shape.device)
+        self._pinned_flags = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._flags_ready = torch.cuda.Event()
+        self._side = torch.cuda.Stream(device=self.shape.device)
         self.update_params()
 
     # refine_3dg_dataset.py:155-159
@@ -89,7 +96,9 @@ class RefineStep:
         id_cap = integ._cap()
         self.bucket.zero_()
         self._sums.zero_()
-        flags = torch.zeros(2, device=shape.device)      # records over capacity / rays cut at the per-ray cap
+        flags = self._flags
+        torch.cuda.current_stream().wait_event(self._flags_ready)     # the previous step's copy of the flags
+        flags.zero_()
         works, images = [], {}
         n_ranges = len(self.ranges)
         for k, vi in enumerate(self.views):
@@ -99,22 +108,37 @@ class RefineStep:
             res = acc.render_forward(params, rays, record=rec, id_cap=id_cap, want_beta=False, want_nhits=False)
             self._pinned_totals[k % self._pinned_totals.shape[0]].copy_(rec.total, non_blocking=True)
             flags += torch.stack([(rec.total[0] > rec.capacity).float(), (rec.total[1] > 0).float()])
+            last = k + 1 == len(self.views)
+            if last:
+                self._post_flags()
             # l1 over the batch film, its gradient and the squared error in one pass (optimizers.py:170-186)
             dL, _ = l1_loss_grad(self.targets[vi], res.rgb.reshape(s.height, s.width, 3), n_total=self.n_pix, sums=self._sums)
             if want_images:
                 images[vi] = res.rgb.reshape(s.height, s.width, 3)
             acc.adjoint_begin(params, rays, dL.reshape(-1, 3), res.rgb, rec, self.bucket.pointers(0))
-            last = k + 1 == len(self.views)
             for c, (p0, p1) in enumerate(self.ranges):
                 acc.adjoint_finish(params, rays, rec, p0, p1, self.bucket.pointers(c))
                 if last and self.world > 1:
                     # the all-reduce of range c runs on NCCL's stream while range c + 1 is still being accumulated
                     works += self.bucket.all_reduce_chunk(c, self.group)
-        if not self.views and self.world > 1:
-            for c in range(n_ranges):
-                works += self.bucket.all_reduce_chunk(c, self.group)
+        if not self.views:
+            self._post_flags()
+            if self.world > 1:
+                for c in range(n_ranges):
+                    works += self.bucket.all_reduce_chunk(c, self.group)
         loss, sq = self._sums[0], self._sums[1]
         return self.bucket, works, ((loss, sq, images, flags) if want_images else (loss, sq, flags))
+
+    def _post_flags(self):
+        """Sum the overflow flags over the ranks and start their copy to pinned memory, on a side stream: the main stream
+        goes on with the adjoint, the host reads the decision as soon as this rank's primal passes are done."""
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            if self.world > 1:
+                dist.all_reduce(self._flags, group=self.group)
+            self._pinned_flags.copy_(self._flags, non_blocking=True)
+            self._flags_ready.record(self._side)
 
     def _step_once(self, want_images):
         acc = self.shape.accel()
@@ -124,24 +148,25 @@ class RefineStep:
         loss, sq, flags = stats_local[0], stats_local[1], stats_local[-1]
         images = stats_local[2] if want_images else None
         ev['compute_done'].record()
-        for w in works:
-            w.wait()
-        ev['comm_done'].record()
         # Every record must have fitted its capacity (the kernels skip an unusable record), and ALL ranks must take
-        # the same decision: the overflow flags travel with the loss statistics.
-        stats = torch.stack([loss, sq, flags[0], flags[1]])
-        if self.world > 1:
-            dist.all_reduce(stats, group=self.group)
-        loss, sq = stats[0], stats[1]
-        torch.cuda.current_stream().synchronize()
+        # the same decision: the flags were summed over the ranks right after the last primal pass, so the host
+        # has them while the GPU is still busy with the adjoint and can queue the optimiser behind it without a gap.
+        self._flags_ready.synchronize()
+        overflowed, cut = self._pinned_flags.tolist()
         if len(self.views):
             entries = int(self._pinned_totals[:len(self.views), 0].max())
             acc.hits_per_ray_estimate = max(4.0, entries / max(self.record.n_rays, 1))
-        _, _, overflowed, cut = stats.tolist()
+        for w in works:
+            w.wait()
+        ev['comm_done'].record()
         if cut:
             raise _cabi.VolprimCudaError("RefineStep: a ray recorded more hits than the integrator's record cap")
         if overflowed:
             return None                # redo the step with records sized from the new estimate
+        stats = torch.stack([loss, sq])
+        if self.world > 1:
+            dist.all_reduce(stats, group=self.group)
+        loss, sq = stats[0], stats[1]
         # identical optimiser step on every rank (refine_3dg_dataset.py:178-189)
         g_data, g_attr, g_sh = self.bucket.gather()
         g = g_data.view(-1, 10)
@@ -149,8 +174,8 @@ class RefineStep:
         o['centers'].grad = g[:, 0:3].contiguous()
         o['scales'].grad = g[:, 3:6].contiguous()
         o['quats'].grad = g[:, 6:10].contiguous()
-        o['opacities'].grad = g_attr.reshape(o['opacities'].shape).clone()
-        o['sh_coeffs'].grad = g_sh.reshape(o['sh_coeffs'].shape).clone()
+        o['opacities'].grad = g_attr.reshape(o['opacities'].shape)      # views of the bucket: valid until the next step
+        o['sh_coeffs'].grad = g_sh.reshape(o['sh_coeffs'].shape)
         o.step()
         self._steps += 1
         self.update_params()
