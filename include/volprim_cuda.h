@@ -249,6 +249,12 @@ VP_API int vp_l1_loss_grad(int64_t n, const float *image, const float *reference
  * *n_internal receives the internal-node count (N-1). */
 VP_API int vp_debug_bvh(vp_ctx *ctx, float *out_nodes, int32_t *out_perm, int64_t *n_internal, void *stream);
 
+/* Device self-test for tests.  which = 0: the correctly rounded shared-reciprocal division used by the exact
+ * ray/ellipsoid intersection (the arithmetic that must equal the reference formulas of common.py:346-367 bit for bit
+ * in fp32) against __fdiv_rn on n pseudo-random operand pairs; *mismatches receives the number of differing results.
+ * Synchronous, current device. */
+VP_API int vp_debug_selftest(int32_t which, int64_t n, uint64_t seed, int64_t *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

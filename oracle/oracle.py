@@ -181,7 +181,7 @@ class Scene:
         nh = np.zeros(R, np.uint32)
         ids = np.full((R, cap), -1, np.int32) if cap else None
         ht = np.full((R, cap), np.inf, np.float64) if cap else None
-        fr = np.zeros((R, 3), np.float64) if fragility else None
+        fr = np.zeros((R, 4), np.float64) if fragility else None
         if fragility:
             params = Params(**{**params.__dict__, "diagnostics": True})
         p = params.to_c()

@@ -668,7 +668,8 @@ static REAL tomo_interact(const orc_scene *sc, const orc_params *pr, int64_t j, 
  * Forward loop.  volprim_rf.py:103-192, volprim_tomography.py:47-127.
  * Outputs (any may be NULL): rgb [R*3]; beta [R]; nhits [R]; hit_ids [R*cap] (-1 padded);
  * hit_t [R*cap] distance of each accepted entry from the ORIGINAL origin (double, diagnostics);
- * fragility [R*3]: per ray min(second_t - t), min |t_near| at the cull, min |discr|.
+ * fragility [R*4]: per ray min(second_t - t), min |t_near| at the cull, min |discr|, min |beta / t_cutoff - 1| after a
+ * hit (volprim_rf only: how close the ray came to flipping the termination test of rf:173-174).
  */
 EXPORT void orc_trace_forward(const orc_scene *sc, const orc_params *pr, int64_t R, const REAL *ray_o,
                               const REAL *ray_d, const REAL *ray_maxt, REAL *rgb, REAL *beta_out, uint32_t *nhits,
@@ -684,7 +685,7 @@ EXPORT void orc_trace_forward(const orc_scene *sc, const orc_params *pr, int64_t
         REAL beta = R_(1), L[3] = { R_(0), R_(0), R_(0) };
         uint32_t depth = 0;
         double tglob = 0.0;
-        double frag[3] = { 1e300, 1e300, 1e300 };
+        double frag[4] = { 1e300, 1e300, 1e300, 1e300 };
         int active = 1;
         if (hit_ids) for (int k = 0; k < cap; ++k) hit_ids[r * cap + k] = -1;
         /* volprim_rf.py:186: the depth test runs at the END of an iteration, so max_depth == 0
@@ -706,6 +707,10 @@ EXPORT void orc_trace_forward(const orc_scene *sc, const orc_params *pr, int64_t
                 rf_interact(sc, pr, h.id, o, d, Y, beta, &q);
                 for (int ch = 0; ch < 3; ++ch) L[ch] = L[ch] + q.Le[ch]; /* rf:145 */
                 beta = beta * q.T;                                       /* rf:146 */
+                if (pr->t_cutoff > 0.0) {
+                    double rel = fabs((double)beta / pr->t_cutoff - 1.0);
+                    if (rel < frag[3]) frag[3] = rel;
+                }
             } else {
                 beta = beta * tomo_interact(sc, pr, h.id, o, d, NULL, NULL); /* tomo:85 */
             }
@@ -736,7 +741,7 @@ EXPORT void orc_trace_forward(const orc_scene *sc, const orc_params *pr, int64_t
         if (rgb) for (int ch = 0; ch < 3; ++ch) rgb[3 * r + ch] = L[ch];
         if (beta_out) beta_out[r] = beta;
         if (nhits) nhits[r] = depth;
-        if (fragility) for (int k = 0; k < 3; ++k) fragility[3 * r + k] = frag[k];
+        if (fragility) for (int k = 0; k < 4; ++k) fragility[4 * r + k] = frag[k];
     }
 }
 

@@ -84,14 +84,17 @@ def robust_mask(res_orc):
     """Rays whose oracle hit list is robust (see compare_forward); the others may legally differ in fp32."""
     frag = res_orc.fragility
     scale = np.maximum(1.0, np.nan_to_num(np.where(np.isfinite(res_orc.hit_t), res_orc.hit_t, 0.0).max(axis=1)))
-    return (frag[:, 0] > 1e-5 * scale) & (frag[:, 1] > 2e-6 * scale) & (frag[:, 2] > 1e-4)
+    # column 3: the throughput came within 1e-5 (relative) of the termination threshold of rf:173-174 -- the list's
+    # LENGTH is then decided by the last bits of the transmittances
+    return (frag[:, 0] > 1e-5 * scale) & (frag[:, 1] > 2e-6 * scale) & (frag[:, 2] > 1e-4) & (frag[:, 3] > 1e-5)
 
 
 def compare_forward(res_gpu, res_orc, cap, max_fragile_frac=5e-3, replay=None, srgb=True, ids_g=None, res_orc64=None):
     """Returns dict of stats; asserts the parity contract.
 
     Contract: for every ray whose hit list the oracle reports as robust (no two entries closer than 1e-5
-    relative, no entry within 1e-6 of the epsilon cull, no |discriminant| below 1e-4), the ID list must be
+    relative, no entry within 1e-6 of the epsilon cull, no |discriminant| below 1e-4, throughput never within 1e-5 of
+    the termination threshold), the ID list must be
     IDENTICAL and radiance / transmittance within tolerance (with `res_orc64`, the float64 oracle's result on the same
     rays, a robust ray must also have the same list in both precisions).  Rays outside that set may differ and are counted;
     their fraction must stay below `max_fragile_frac`, and with `replay` = (oracle scene, oracle params, o, d, maxt)

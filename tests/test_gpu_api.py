@@ -21,6 +21,19 @@ def _sensor_dict(cam, rfilter="box"):
             "film": {"type": "hdrfilm", "width": cam.width, "height": cam.height, "rfilter": {"type": rfilter}}}
 
 
+def test_shared_reciprocal_division_is_correctly_rounded():
+    """exact_isect's divisions share reciprocals (vp_div_rn); the hit ORDER rests on them being the IEEE quotients the
+    oracle's C code computes.  2^28 random operand pairs of the magnitudes that occur there, against __fdiv_rn."""
+    import ctypes as C
+    from volprim_balance_b200 import _cabi
+    lib = _cabi.load_library()
+    torch.cuda.set_device(0)
+    for seed in (1, 0xC0FFEE):
+        bad = C.c_int64(-1)
+        _cabi.check(lib.vp_debug_selftest(0, 1 << 27, seed, C.byref(bad)))
+        assert bad.value == 0, f"{bad.value} of 2^27 quotients differ from __fdiv_rn"
+
+
 def test_raygen_matches_perspective_sensor_restatement():
     cam = synthetic.ring_camera(3, 8, 72, 40)
     acc = gpu_scene(synthetic.make_cloud(4, 0.1, seed=0))

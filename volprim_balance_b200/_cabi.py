@@ -129,6 +129,7 @@ SIGNATURES = {
                                        C.c_int, C.c_float, C.c_int, C.c_float, _VP]),
     "vp_l1_loss_grad": (C.c_int, [C.c_int64, _VP, _VP, C.c_double, _VP, _VP, _VP]),
     "vp_debug_bvh": (C.c_int, [_VP, _VP, _VP, C.POINTER(C.c_int64), _VP]),
+    "vp_debug_selftest": (C.c_int, [C.c_int32, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -83,6 +83,27 @@ DevScene vp_dev_scene(const vp_ctx *ctx)
     return S;
 }
 
+// vp_debug_selftest(0): the shared-reciprocal division of exact_isect (vp_div_rn) against __fdiv_rn on pseudo-random
+// operands of the magnitudes that occur there (numerators 2^-40 .. 2^20, denominators 2^-24 .. 2^10, both signs)
+__global__ void k_selftest_div(int64_t n, uint64_t seed, unsigned long long *mismatches)
+{
+    unsigned long long bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + 0x9e3779b97f4a7c15ull * (uint64_t)(i + 1);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        z ^= z >> 31;
+        const uint32_t lo = (uint32_t)z, hi = (uint32_t)(z >> 32);
+        const uint32_t ea = 127u - 40u + (lo >> 23) % 61u, eb = 127u - 24u + (hi >> 23) % 35u;
+        const float a = __uint_as_float((lo & 0x807fffffu) | (ea << 23));
+        const float b = __uint_as_float((hi & 0x807fffffu) | (eb << 23));
+        const float want = __fdiv_rn(a, b);
+        const float got = vp_div_rn(a, vp_divisor(b));
+        bad += __float_as_uint(want) != __float_as_uint(got);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 extern "C" {
 
 int vp_version(void) { return VP_VERSION; }
@@ -286,6 +307,21 @@ int vp_debug_bvh(vp_ctx *ctx, float *out_nodes, int32_t *out_perm, int64_t *n_in
         VP_CUDA_CHECK(ctx, cudaMemcpyAsync(out_nodes, ctx->nodes.ptr, sizeof(float) * 16 * (size_t)ni, cudaMemcpyDeviceToDevice, st));
     if (out_perm && ctx->n > 0)
         VP_CUDA_CHECK(ctx, cudaMemcpyAsync(out_perm, ctx->perm.ptr, sizeof(int32_t) * (size_t)ctx->n, cudaMemcpyDeviceToDevice, st));
+    return VP_OK;
+}
+
+int vp_debug_selftest(int32_t which, int64_t n, uint64_t seed, int64_t *mismatches)
+{
+    if (which != 0 || n < 0 || !mismatches) return VP_E_INVALID;
+    unsigned long long *d = nullptr;
+    if (cudaMalloc(&d, sizeof *d) != cudaSuccess) return VP_E_CUDA;
+    cudaMemset(d, 0, sizeof *d);
+    k_selftest_div<<<148 * 8, 256>>>(n, seed, d);
+    unsigned long long h = 0;
+    const cudaError_t e = cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return VP_E_CUDA;
+    *mismatches = (int64_t)h;
     return VP_OK;
 }
 

@@ -31,6 +31,20 @@
 #include <cfloat>
 #include <cmath>
 
+// Value-path arithmetic.  Everything that ORDERS hits or applies the epsilon cull is evaluated with individually
+// rounded operations (exact_isect); everything else -- the transmittance of a hit, the ordering keys of the candidate
+// lists (re-decided by the exact test), the conservative culls -- may use approximate reciprocals, roots and ex2
+// (2 ulp).  IEEE divisions / roots / expf in those places cost the issue-bound forward kernel 12 % (measured).
+#ifndef VP_EVAL_FAST
+#define VP_EVAL_FAST 1
+#endif
+#ifndef VP_APPROX_ORDER
+#define VP_APPROX_ORDER 1
+#endif
+#ifndef VP_DIV_SHARED
+#define VP_DIV_SHARED 1
+#endif
+
 namespace {
 
 #ifndef VP_CAND_CAP
@@ -106,12 +120,24 @@ __device__ __forceinline__ Isect exact_isect(float3 o, float3 d, float4 g0, floa
     float3 v = make_float3(__fsub_rn(o.x, g0.x), __fsub_rn(o.y, g0.y), __fsub_rn(o.z, g0.z));
     r.rd = vp_rot_t_mul_rn(R, d);
     r.ro = vp_rot_t_mul_rn(R, v);
+#if VP_DIV_SHARED
+    // six divisions over three denominators, then three more: shared reciprocals, same bits (vp_internal.cuh)
+    const VpDivisor dx = vp_divisor(sc.x), dy = vp_divisor(sc.y), dz = vp_divisor(sc.z);
+    float3 dd = make_float3(vp_div_rn(r.rd.x, dx), vp_div_rn(r.rd.y, dy), vp_div_rn(r.rd.z, dz));
+    float3 oo = make_float3(vp_div_rn(r.ro.x, dx), vp_div_rn(r.ro.y, dy), vp_div_rn(r.ro.z, dz));
+#else
     float3 dd = make_float3(__fdiv_rn(r.rd.x, sc.x), __fdiv_rn(r.rd.y, sc.y), __fdiv_rn(r.rd.z, sc.z));
     float3 oo = make_float3(__fdiv_rn(r.ro.x, sc.x), __fdiv_rn(r.ro.y, sc.y), __fdiv_rn(r.ro.z, sc.z));
+#endif
     float a = vp_dot_rn(dd, dd);
     float b = -vp_dot_rn(oo, dd);
     float c = __fsub_rn(vp_dot_rn(oo, oo), 1.f);
+#if VP_DIV_SHARED
+    const VpDivisor da = vp_divisor(a);
+    float ba = vp_div_rn(b, da);
+#else
     float ba = __fdiv_rn(b, a);
+#endif
     float3 l = make_float3(__fadd_rn(oo.x, __fmul_rn(ba, dd.x)), __fadd_rn(oo.y, __fmul_rn(ba, dd.y)),
                            __fadd_rn(oo.z, __fmul_rn(ba, dd.z)));
     float discr = __fsub_rn(1.f, vp_dot_rn(l, l));
@@ -120,8 +146,13 @@ __device__ __forceinline__ Isect exact_isect(float3 o, float3 d, float4 g0, floa
     if (!(discr >= 0.f) || a == 0.f) return r;
     float sq = __fsqrt_rn(__fmul_rn(a, discr));
     float q = __fadd_rn(b, copysignf(sq, b));
+#if VP_DIV_SHARED
+    float x0 = vp_div_rn(c, vp_divisor(q));
+    float x1 = vp_div_rn(q, da);
+#else
     float x0 = __fdiv_rn(c, q);
     float x1 = __fdiv_rn(q, a);
+#endif
     r.tn = fminf(x0, x1);
     r.tf = fmaxf(x0, x1);
     r.valid = isfinite(x0) && isfinite(x1);
@@ -172,7 +203,12 @@ __device__ __forceinline__ bool fast_isect(const DevScene &S, int pos, float3 o,
     // also a small difference of terms of size |o'|^2.  A grazing hit must never be lost here -- false candidates only
     // cost one exact test in the drain (0.5 % of the candidates have |discr| < 1e-2).
     if (!(discr >= -(1e-2f + 2e-6f * (fabsf(oo.x) + fabsf(oo.y) + fabsf(oo.z)))) || !(a > 0.f)) return false;
+#if VP_APPROX_ORDER
+    const float ad = a * fmaxf(discr, 0.f);
+    float sq = ad * rsqrtf(fmaxf(ad, 1e-37f));      // 2 ulp: the ordering key needs 1e-6, the exact test decides
+#else
     float sq = sqrtf(a * fmaxf(discr, 0.f));
+#endif
     float q = b + copysignf(sq, b);
     float x0 = __fdividef(c, q), x1 = __fdividef(q, a);
     tn = fminf(x0, x1) + t_base;
@@ -243,6 +279,22 @@ __device__ __forceinline__ void list_insert_key(unsigned long long *s_key, int n
     s_key[j * STRIDE] = key;
 }
 
+// An on_hit callable may carry a preload(pos) hook: it is called as soon as the entry's position is known, before the
+// exact intersection, so that loads the hit will need (the head of its SH block) are in flight during those ~200
+// instructions instead of being issued after them.
+template <class F, class P>
+struct HitWithPreload {
+    F f;
+    P p;
+    template <class... Args>
+    __device__ __forceinline__ bool operator()(Args &&...args) { return f(static_cast<Args &&>(args)...); }
+    __device__ __forceinline__ void preload(int pos) { p(pos); }
+};
+template <class T, class = void>
+struct has_preload { static constexpr bool value = false; };
+template <class T>
+struct has_preload<T, decltype(void(&T::preload))> { static constexpr bool value = true; };
+
 template <class GetPos, class OnHit>
 __device__ __forceinline__ void drain_list(const DevScene &S, int n_found, GetPos &&get_pos, const float3 &o,
                                            const float3 d, float maxt, bool &alive, bool &missed, OnHit &&on_hit)
@@ -255,6 +307,7 @@ __device__ __forceinline__ void drain_list(const DevScene &S, int n_found, GetPo
         const int pos = get_pos(k);
         VP_CHECK(pos >= 0 && pos < S.n, 6, pos, k);
         float4 g0 = __ldg(S.geo0 + pos), g1 = __ldg(S.geo1 + pos), g2 = __ldg(S.geo2 + pos);
+        if constexpr (has_preload<typename std::remove_reference<OnHit>::type>::value) on_hit.preload(pos);
         Mat3 Rm = vp_quat_to_matrix_rn(g2);
         Isect is = exact_isect(o, d, g0, g1, Rm, S.extent);
         if (!is.valid || !(is.tn > 0.f)) continue;      // entry fell behind the advanced origin (Q1)
@@ -447,7 +500,7 @@ struct Capsule {
 __device__ __forceinline__ Capsule tile_capsule(bool alive, unsigned am, float3 o0, float3 d, float t0, float t1)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    const float inv_n = 1.f / (float)__popc(am);
+    const float inv_n = __fdividef(1.f, (float)__popc(am));
     float3 P0 = make_float3(fmaf(d.x, t0, o0.x), fmaf(d.y, t0, o0.y), fmaf(d.z, t0, o0.z));
     float3 P1 = make_float3(fmaf(d.x, t1, o0.x), fmaf(d.y, t1, o0.y), fmaf(d.z, t1, o0.z));
     float3 A = alive ? P0 : make_float3(0.f, 0.f, 0.f), B = alive ? P1 : make_float3(0.f, 0.f, 0.f);
@@ -460,15 +513,16 @@ __device__ __forceinline__ Capsule tile_capsule(bool alive, unsigned am, float3 
     if (alive) {
         float e0 = (P0.x - A.x) * (P0.x - A.x) + (P0.y - A.y) * (P0.y - A.y) + (P0.z - A.z) * (P0.z - A.z);
         float e1 = (P1.x - B.x) * (P1.x - B.x) + (P1.y - B.y) * (P1.y - B.y) + (P1.z - B.z) * (P1.z - B.z);
-        r = sqrtf(fmaxf(e0, e1));
+        const float e = fmaxf(e0, e1);
+        r = e * rsqrtf(fmaxf(e, 1e-37f));      // (the 1.0001 margin below covers the approximation)
     }
     for (int off = 16; off; off >>= 1) r = fmaxf(r, __shfl_xor_sync(FULL, r, off));
     Capsule c;
     c.r = r * 1.0001f + 1e-6f * (1.f + fabsf(A.x) + fabsf(A.y) + fabsf(A.z));
     float3 Dx = make_float3(B.x - A.x, B.y - A.y, B.z - A.z);
-    c.invD.x = 1.f / (fabsf(Dx.x) > 1e-30f ? Dx.x : copysignf(1e-30f, Dx.x));
-    c.invD.y = 1.f / (fabsf(Dx.y) > 1e-30f ? Dx.y : copysignf(1e-30f, Dx.y));
-    c.invD.z = 1.f / (fabsf(Dx.z) > 1e-30f ? Dx.z : copysignf(1e-30f, Dx.z));
+    c.invD.x = __fdividef(1.f, fabsf(Dx.x) > 1e-30f ? Dx.x : copysignf(1e-30f, Dx.x));
+    c.invD.y = __fdividef(1.f, fabsf(Dx.y) > 1e-30f ? Dx.y : copysignf(1e-30f, Dx.y));
+    c.invD.z = __fdividef(1.f, fabsf(Dx.z) > 1e-30f ? Dx.z : copysignf(1e-30f, Dx.z));
     c.AI = make_float3(A.x * c.invD.x, A.y * c.invD.y, A.z * c.invD.z);
     return c;
 }
@@ -483,7 +537,7 @@ struct TilePrism {
 __device__ __forceinline__ TilePrism tile_prism(bool alive, unsigned am, float3 o0, float3 d, float t0, float t1)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    const float inv_n = 1.f / (float)__popc(am);
+    const float inv_n = __fdividef(1.f, (float)__popc(am));
     const float3 P0 = make_float3(fmaf(d.x, t0, o0.x), fmaf(d.y, t0, o0.y), fmaf(d.z, t0, o0.z));
     const float3 P1 = make_float3(fmaf(d.x, t1, o0.x), fmaf(d.y, t1, o0.y), fmaf(d.z, t1, o0.z));
     float3 A = alive ? P0 : make_float3(0.f, 0.f, 0.f), B = alive ? P1 : make_float3(0.f, 0.f, 0.f);
@@ -545,12 +599,23 @@ __device__ __forceinline__ bool prism_may_hit(const DevScene &S, int pos, const 
                                   r2.x * p.D.x + r2.y * p.D.y + r2.z * p.D.z);
     const float dd = Dp.x * Dp.x + Dp.y * Dp.y + Dp.z * Dp.z;
     if (!(dd > 1e-30f)) return true;
+#if VP_APPROX_ORDER
+    // approximate reciprocal / root: 2 ulp on k is covered by `err` below, lam only sorts candidates into buckets
+    const float idd = __fdividef(1.f, dd);
+    const float k = (Ap.x * Dp.x + Ap.y * Dp.y + Ap.z * Dp.z) * idd;
+#else
     const float k = (Ap.x * Dp.x + Ap.y * Dp.y + Ap.z * Dp.z) / dd;
+#endif
     const float3 P = make_float3(Ap.x - k * Dp.x, Ap.y - k * Dp.y, Ap.z - k * Dp.z);
     const float pl2 = P.x * P.x + P.y * P.y + P.z * P.z;
     lam = -k;
     if (!(pl2 > 1.f)) {                     // the mean line itself passes through the bounding ellipsoid
+#if VP_APPROX_ORDER
+        const float x = (1.f - pl2) * idd;
+        lam -= x * rsqrtf(fmaxf(x, 1e-37f));
+#else
         lam -= sqrtf((1.f - pl2) / dd);
+#endif
         return true;
     }
     const float ipl = rsqrtf(pl2), pl = pl2 * ipl;
@@ -829,10 +894,10 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         else {
             const float fill_h = (float)found_max * (1.f / (VP_FILL * TILE_HIT_CAP));
             const float fill_c = (float)tcn * (1.f / (float)(VP_CAND_TARGET));
-            const float f_h = (fill_h < 0.15f) ? VP_GROW_MAX : fminf(fmaxf(1.f / fill_h, 0.5f), 2.f);
+            const float f_h = (fill_h < 0.15f) ? VP_GROW_MAX : fminf(fmaxf(__fdividef(1.f, fill_h), 0.5f), 2.f);
             // the candidate count only shrinks the interval while that can help: boxes that contain the whole
             // neighbourhood (nested primitives) stay candidates however short the interval gets
-            const float f_c = fmaxf(1.f / fmaxf(fill_c, 0.25f), delta > delta0 * (1.f / VP_CSHRINK_FLOOR) ? 0.5f : 1.f);
+            const float f_c = fmaxf(__fdividef(1.f, fmaxf(fill_c, 0.25f)), delta > delta0 * (1.f / VP_CSHRINK_FLOOR) ? 0.5f : 1.f);
             delta = fmaxf(delta * fminf(f_h, f_c), delta_floor);
         }
         t_start = t_done;
@@ -922,8 +987,32 @@ __device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b)
 
 // eval_sh_emission (rf:82-100): raw = sum_i Y_i f_i + 0.5 ; col = max(raw, 0).  128-bit loads of the
 // primitive's contiguous coefficient block.
+// how many leading float4 of the SH block the forward drain fetches before the exact intersection (VP_SH_HOIST)
+#ifndef VP_SH_HOIST
+#define VP_SH_HOIST 2
+#endif
 template <int D>
-__device__ __forceinline__ void sh_color(const DevScene &S, int pos, const float (&Y)[(D + 1) * (D + 1)], float (&raw)[3])
+struct ShHead {
+    static constexpr int N4 = (3 * (D + 1) * (D + 1) + 3) / 4;
+    static constexpr int PRE = (N4 % 2 == 0 && VP_SH_HOIST <= N4) ? VP_SH_HOIST : 0;     // even block sizes only (256-bit loads)
+    float4 v[PRE > 0 ? PRE : 1];
+    __device__ __forceinline__ void load(const DevScene &S, int pos)
+    {
+        if constexpr (PRE > 0) {
+            const float4 *f = S.sh4 + (size_t)pos * N4;
+#pragma unroll
+            for (int k = 0; k < PRE; k += 2)
+                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w), "=f"(v[k + 1].x), "=f"(v[k + 1].y),
+                               "=f"(v[k + 1].z), "=f"(v[k + 1].w)
+                             : "l"(f + k));
+        }
+    }
+};
+
+template <int D>
+__device__ __forceinline__ void sh_color(const DevScene &S, int pos, const float (&Y)[(D + 1) * (D + 1)], float (&raw)[3],
+                                         const ShHead<D> *head = nullptr)
 {
     constexpr int NB = (D + 1) * (D + 1);
     constexpr int C = 3 * NB;
@@ -931,6 +1020,27 @@ __device__ __forceinline__ void sh_color(const DevScene &S, int pos, const float
     const float4 *f = S.sh4 + (size_t)pos * N4;
     float acc[3] = { 0.f, 0.f, 0.f };
     float4 v[N4];
+    if constexpr (ShHead<D>::PRE > 0) {
+        if (head) {
+            constexpr int PRE = ShHead<D>::PRE;
+#pragma unroll
+            for (int k = PRE; k < N4; k += 2) ldg256(f + k, v[k], v[k + 1]);
+#pragma unroll
+            for (int k = 0; k < PRE; ++k) v[k] = head->v[k];
+#pragma unroll
+            for (int k = 0; k < N4; ++k) {
+                const float e[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int idx = 4 * k + c;
+                    if (idx < C) acc[idx % 3] = fmaf(Y[idx / 3], e[c], acc[idx % 3]);
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) raw[ch] = acc[ch] + 0.5f;
+            return;
+        }
+    }
 #ifdef VP_SH_LDG256
     // sm_100 has 256-bit global loads: the coefficient block of a primitive (192 B at degree 3, 32-byte aligned when
     // N4 is even) takes half as many load instructions -- and half as many L1 wavefronts, the co-limiter of the drain
@@ -991,6 +1101,27 @@ __device__ __forceinline__ RfEval rf_eval(float3 o, float3 d, float4 g0, float4 
     return e;
 }
 
+// The primal pass needs only T of eval_transmission (rf:63-80).  With u = R^T (p_peak - c) / s = o' + t_peak d' (o', d'
+// the ray in the primitive's scaled frame, which exact_isect has already rotated) the kernel value is a function of
+// |u|^2 alone: approximate reciprocals and ex2 are enough here (errors ~1e-6 of T; nothing orders hits).
+template <int KERNEL>
+__device__ __forceinline__ float rf_transmittance(float4 g0, float4 g1, const Isect &is)
+{
+    const float isx = __fdividef(1.f, g1.x), isy = __fdividef(1.f, g1.y), isz = __fdividef(1.f, g1.z);
+    const float3 oo = make_float3(is.ro.x * isx, is.ro.y * isy, is.ro.z * isz);
+    const float3 dd = make_float3(is.rd.x * isx, is.rd.y * isy, is.rd.z * isz);
+    const float od = fmaf(oo.x, dd.x, fmaf(oo.y, dd.y, oo.z * dd.z)), dd2 = fmaf(dd.x, dd.x, fmaf(dd.y, dd.y, dd.z * dd.z));
+    const float tp = -__fdividef(od, dd2);
+    const float ux = fmaf(tp, dd.x, oo.x), uy = fmaf(tp, dd.y, oo.y), uz = fmaf(tp, dd.z, oo.z);
+    const float q = fmaf(ux, ux, fmaf(uy, uy, uz * uz));
+    float G;
+    if (KERNEL == VP_KERNEL_GAUSSIAN) G = __expf(-0.5f * q);
+    else G = fmaxf(0.75f * (1.f - q * (1.f / 9.f)), 0.f);
+    float a = g0.w * G;
+    if (!(a < 0.9999f)) a = 0.9999f;
+    return 1.f - a;
+}
+
 // quat_to_matrix / R^T v with fused multiply-adds (value paths of the adjoint; nothing here decides hit order)
 __device__ __forceinline__ Mat3 quat_to_matrix_fast(float4 q)
 {
@@ -1024,10 +1155,11 @@ template <int KERNEL>
 __device__ __forceinline__ RfEval rf_eval_far(float3 o, float3 d, float4 g0, float4 g1, const Mat3 &R)
 {
     RfEval e;
-    const float isx = 1.f / g1.x, isy = 1.f / g1.y, isz = 1.f / g1.z;
+    // approximate reciprocals / ex2 (2 ulp): a value path, nothing here orders hits
+    const float isx = __fdividef(1.f, g1.x), isy = __fdividef(1.f, g1.y), isz = __fdividef(1.f, g1.z);
     const float3 rd = rot_t_mul_fast(R, d);
     const float3 dd = make_float3(rd.x * isx, rd.y * isy, rd.z * isz);
-    const float inv_dd2 = 1.f / fmaf(dd.x, dd.x, fmaf(dd.y, dd.y, dd.z * dd.z));
+    const float inv_dd2 = __fdividef(1.f, fmaf(dd.x, dd.x, fmaf(dd.y, dd.y, dd.z * dd.z)));
     float3 ro = rot_t_mul_fast(R, make_float3(o.x - g0.x, o.y - g0.y, o.z - g0.z));
     const float t0 = -fmaf(ro.x * isx, dd.x, fmaf(ro.y * isy, dd.y, ro.z * isz * dd.z)) * inv_dd2;
     const float3 o1 = make_float3(fmaf(d.x, t0, o.x), fmaf(d.y, t0, o.y), fmaf(d.z, t0, o.z));
@@ -1037,7 +1169,7 @@ __device__ __forceinline__ RfEval rf_eval_far(float3 o, float3 d, float4 g0, flo
     const float3 w = rot_t_mul_fast(R, make_float3(e.pp.x - g0.x, e.pp.y - g0.y, e.pp.z - g0.z));
     if (KERNEL == VP_KERNEL_GAUSSIAN) {
         const float ux = w.x * isx, uy = w.y * isy, uz = w.z * isz;
-        e.G = expf(-0.5f * fmaf(ux, ux, fmaf(uy, uy, uz * uz)));
+        e.G = __expf(-0.5f * fmaf(ux, ux, fmaf(uy, uy, uz * uz)));
     } else {
         const float ux = w.x * isx * (1.f / 3.f), uy = w.y * isy * (1.f / 3.f), uz = w.z * isz * (1.f / 3.f);
         e.G = fmaxf(0.75f * (1.f - fmaf(ux, ux, fmaf(uy, uy, uz * uz))), 0.f);
@@ -1296,18 +1428,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
     uint32_t depth = 0;
     bool missed = false;
 
-    auto on_hit = [&](int pos, float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is) -> bool {
+    ShHead<(D >= 0 ? D : 0)> sh_head;
+    auto on_hit_body = [&](int pos, float4 g0, float4 g1, float4 g2, const Mat3 &Rm, const Isect &is) -> bool {
         float T;
         if constexpr (INTEG == VP_INTEGRATOR_RF) {
+#if VP_EVAL_FAST
+            T = rf_transmittance<KERNEL>(g0, g1, is);
+#else
             RfEval e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
             T = e.T;
+#endif
             float raw[3] = { 0.f, 0.f, 0.f };
             if constexpr (D >= 0) {
                 // the SH basis is re-evaluated per hit (~35 instructions) instead of holding 16 registers across the
                 // whole walk: lower register pressure buys a sixth resident block per SM
                 float Y[(D >= 0) ? (D + 1) * (D + 1) : 1];
                 sh_basis<(D >= 0 ? D : 0)>(d, Y);
-                sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw);
+                sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw, &sh_head);
             }
             const float omt = 1.f - T;
             float col[3];
@@ -1353,6 +1490,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, VP_MIN_BLOCKS) k_trace_forward(
         if (!(depth < P.max_depth)) return false;                             // rf:186
         return true;
     };
+    auto on_pre = [&](int pos) {
+        if constexpr (INTEG == VP_INTEGRATOR_RF && D >= 0) sh_head.load(S, pos);
+    };
+    HitWithPreload<decltype(on_hit_body) &, decltype(on_pre) &> on_hit{ on_hit_body, on_pre };
     if constexpr (TILE) walk_tile(S, reinterpret_cast<int *>(smem_raw), o, o0, d, maxt, in_range, missed, cn, on_hit);
     else walk_ray(S, s_id, s_t, o, o0, d, maxt, in_range, missed, cn, on_hit);
 
@@ -1417,7 +1558,13 @@ __device__ __forceinline__ RfCoeffs rf_adjoint_coeffs(const DevScene &S, int pos
     RfCoeffs c;
     RfEval e;
     if constexpr (FAR) e = rf_eval_far<KERNEL>(o, d, g0, g1, Rm);
-    else e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
+    else {
+        e = rf_eval<KERNEL>(o, d, g0, g1, Rm, is);
+#if VP_EVAL_FAST
+        // the transmittance the primal pass used, bit for bit: a re-walking adjoint must terminate where it did
+        e.T = rf_transmittance<KERNEL>(g0, g1, is);
+#endif
+    }
     float raw[3] = { 0.f, 0.f, 0.f };
     if constexpr (D >= 0) sh_color<(D >= 0 ? D : 0)>(S, pos, Y, raw);
     const float omt = 1.f - e.T;
@@ -1455,9 +1602,10 @@ __device__ __forceinline__ bool rf_geo_terms(float4 g0, float4 g1, const Mat3 &R
     else { dq = (G > 0.f) ? -0.75f * dG : 0.f; k2 = 9.f; }
     if (dq == 0.f) return false;
     v = make_float3(pp.x - g0.x, pp.y - g0.y, pp.z - g0.z);
-    w = vp_rot_t_mul_rn(Rm, v);
-    const float sx2 = k2 * g1.x * g1.x, sy2 = k2 * g1.y * g1.y, sz2 = k2 * g1.z * g1.z;
-    dw[0] = 2.f * w.x / sx2 * dq; dw[1] = 2.f * w.y / sy2 * dq; dw[2] = 2.f * w.z / sz2 * dq;
+    w = rot_t_mul_fast(Rm, v);
+    // reciprocals of per-primitive constants: loop-invariant in the primitive-major pass
+    const float ix2 = __fdividef(2.f, k2 * g1.x * g1.x), iy2 = __fdividef(2.f, k2 * g1.y * g1.y), iz2 = __fdividef(2.f, k2 * g1.z * g1.z);
+    dw[0] = w.x * ix2 * dq; dw[1] = w.y * iy2 * dq; dw[2] = w.z * iz2 * dq;
     return true;
 }
 
@@ -1958,6 +2106,8 @@ __device__ __forceinline__ void prb_step(float4 st, const float (&g)[3], float (
 {
     const float T = st.w, omt = 1.f - T;
     const float col[3] = { st.x, st.y, st.z };
+    // one approximate reciprocal per hit instead of six IEEE divisions (T = 0 -> inf -> NaN below, as the literal form)
+    const float inv_t = __fdividef(1.f, T);
     dalpha = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
@@ -1965,14 +2115,14 @@ __device__ __forceinline__ void prb_step(float4 st, const float (&g)[3], float (
         const bool lef = isfinite(le);
         if (!lef) le = 0.f;
         L[ch] -= le;                                  // rf:145 (adjoint branch)
-        const float lo = le + L[ch] * T / T;          // rf:156-159
+        const float lo = le + L[ch] * T * inv_t;      // rf:156-159
         dcol[ch] = 0.f;
         if (isfinite(lo)) {                           // rf:160
             if (lef) {
                 dalpha += g[ch] * beta * col[ch];
                 if (col[ch] > 0.f) dcol[ch] = g[ch] * beta * omt;
             }
-            dalpha -= g[ch] * L[ch] / T;
+            dalpha -= g[ch] * L[ch] * inv_t;
         }
     }
     if (!(T > 1.f - 0.9999f)) dalpha = 0.f;           // alpha was clamped (rf:76): no gradient to opacity / geometry
