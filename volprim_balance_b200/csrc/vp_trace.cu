@@ -44,6 +44,9 @@
 #ifndef VP_DIV_SHARED
 #define VP_DIV_SHARED 1
 #endif
+#ifndef VP_RANKS_MATCH
+#define VP_RANKS_MATCH 1
+#endif
 
 namespace {
 
@@ -2084,18 +2087,49 @@ __global__ void __launch_bounds__(256) k_bucket_ranks(const int32_t *__restrict_
 }
 
 // the same over a DENSE hit-major record ([id_cap][n_rays], entry (k, r) valid for k < counts[r]): one thread per ray,
-// reads and rank writes coalesced across the warp
+// reads and rank writes coalesced across the warp.  The 32 rays of a warp are neighbours and share primitives at equal
+// depth, and the pass is bound by the throughput of value-returning atomics: lanes with the same primitive are grouped
+// (__match_any_sync), the group's first lane adds the group size once and hands out consecutive ranks.  Four depths are
+// in flight per round so that the atomics' latency overlaps.
 __global__ void __launch_bounds__(256) k_bucket_ranks_dense(const int32_t *__restrict__ ids, const uint32_t *__restrict__ ray_counts,
                                                             int64_t n_rays, const int64_t *__restrict__ total, int64_t capacity,
                                                             uint32_t *__restrict__ counts, uint32_t *__restrict__ rank)
 {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int U = 4;
     if (total[0] > capacity || total[1] != 0) return;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rays) return;
-    const uint32_t c = ray_counts[r];
-    for (uint32_t k = 0; k < c; ++k) {
-        const int64_t e = (int64_t)k * n_rays + r;
-        rank[e] = atomicAdd(counts + ids[e], 1u);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t c = r < n_rays ? ray_counts[r] : 0u;       // (no early exit: the warp stays convergent for the matches)
+    const uint32_t cmax = __reduce_max_sync(FULL, c);
+    for (uint32_t k0 = 0; k0 < cmax; k0 += U) {
+        int32_t id[U];
+        unsigned grp[U];
+        uint32_t base[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) id[u] = (k0 + u < c) ? __ldcs(ids + (int64_t)(k0 + u) * n_rays + r) : -1;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned act = __ballot_sync(FULL, id[u] >= 0);
+            grp[u] = 0u;
+            base[u] = 0u;
+            if (id[u] >= 0) {
+#if VP_RANKS_MATCH
+                grp[u] = __match_any_sync(act, id[u]);
+#else
+                grp[u] = 1u << lane;
+#endif
+                if ((grp[u] & lt) == 0u) base[u] = atomicAdd(counts + id[u], (uint32_t)__popc(grp[u]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (id[u] >= 0) {
+                const uint32_t b = __shfl_sync(grp[u], base[u], __ffs(grp[u]) - 1);
+                rank[(int64_t)(k0 + u) * n_rays + r] = b + (uint32_t)__popc(grp[u] & lt);
+            }
+        }
     }
 }
 
