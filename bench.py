@@ -57,7 +57,7 @@ WORKLOADS = {
                  mu_opacity=-4.0, max_depth=-1, desc="stress: 10M overlapping Gaussian ellipsoids SH3, 3840x2160, "
                                                      "~200 hits/ray, max_depth=-1 (BASELINE configs[4])"),
 }
-VIEWS_PER_STEP = 24        # one step = this many views (a >= 2 s timed region at the driver's 20 steps)
+VIEWS_PER_STEP = 32        # one step = this many views (a >= 2 s timed region at the driver's 20 steps)
 TRAIN_VIEWS = 8            # fixed global batch of the training step (BASELINE configs[3]: 8 views / step)
 RAY_IO_BYTES = 44          # 28 B read (o, d, maxt) + 16 B written (rgb, T)        BASELINE.md section 5
 EVAL_BYTES_SH3 = 236       # 40 geometry + 4 opacity + 192 SH per primitive evaluation
@@ -695,7 +695,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--views-per-step", type=int, default=0, help="views per step (default: 24 for cfg2, fewer for the larger workloads)")
+    ap.add_argument("--views-per-step", type=int, default=0, help="views per step (default: 32 for cfg2, fewer for the larger workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg3 (north-star) and build-time measurements")
