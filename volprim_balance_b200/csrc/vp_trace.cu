@@ -198,7 +198,8 @@ __device__ __forceinline__ bool fast_isect(const DevScene &S, int pos, float3 o,
     float a = dd.x * dd.x + dd.y * dd.y + dd.z * dd.z;
     float b = -(oo.x * dd.x + oo.y * dd.y + oo.z * dd.z);
     float c = oo.x * oo.x + oo.y * oo.y + oo.z * oo.z - 1.f;
-    float ba = __fdividef(b, a);
+    const float ia = vp_rcp(a);
+    float ba = b * ia;
     float lx = fmaf(ba, dd.x, oo.x), ly = fmaf(ba, dd.y, oo.y), lz = fmaf(ba, dd.z, oo.z);
     float discr = 1.f - (lx * lx + ly * ly + lz * lz);
     // Conservative validity: the interval origin sits on the world-coordinate grid, up to 2^-24 |o| beside the ray, and
@@ -208,12 +209,12 @@ __device__ __forceinline__ bool fast_isect(const DevScene &S, int pos, float3 o,
     if (!(discr >= -(1e-2f + 2e-6f * (fabsf(oo.x) + fabsf(oo.y) + fabsf(oo.z)))) || !(a > 0.f)) return false;
 #if VP_APPROX_ORDER
     const float ad = a * fmaxf(discr, 0.f);
-    float sq = ad * rsqrtf(fmaxf(ad, 1e-37f));      // 2 ulp: the ordering key needs 1e-6, the exact test decides
+    float sq = ad * vp_rsqrt(fmaxf(ad, 1e-37f));      // 2 ulp: the ordering key needs 1e-6, the exact test decides
 #else
     float sq = sqrtf(a * fmaxf(discr, 0.f));
 #endif
     float q = b + copysignf(sq, b);
-    float x0 = __fdividef(c, q), x1 = __fdividef(q, a);
+    float x0 = c * vp_rcp(q), x1 = q * ia;
     tn = fminf(x0, x1) + t_base;
     return tn == tn;
 }
@@ -503,7 +504,7 @@ struct Capsule {
 __device__ __forceinline__ Capsule tile_capsule(bool alive, unsigned am, float3 o0, float3 d, float t0, float t1)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    const float inv_n = __fdividef(1.f, (float)__popc(am));
+    const float inv_n = vp_rcp((float)__popc(am));
     float3 P0 = make_float3(fmaf(d.x, t0, o0.x), fmaf(d.y, t0, o0.y), fmaf(d.z, t0, o0.z));
     float3 P1 = make_float3(fmaf(d.x, t1, o0.x), fmaf(d.y, t1, o0.y), fmaf(d.z, t1, o0.z));
     float3 A = alive ? P0 : make_float3(0.f, 0.f, 0.f), B = alive ? P1 : make_float3(0.f, 0.f, 0.f);
@@ -517,15 +518,15 @@ __device__ __forceinline__ Capsule tile_capsule(bool alive, unsigned am, float3 
         float e0 = (P0.x - A.x) * (P0.x - A.x) + (P0.y - A.y) * (P0.y - A.y) + (P0.z - A.z) * (P0.z - A.z);
         float e1 = (P1.x - B.x) * (P1.x - B.x) + (P1.y - B.y) * (P1.y - B.y) + (P1.z - B.z) * (P1.z - B.z);
         const float e = fmaxf(e0, e1);
-        r = e * rsqrtf(fmaxf(e, 1e-37f));      // (the 1.0001 margin below covers the approximation)
+        r = e * vp_rsqrt(fmaxf(e, 1e-37f));      // (the 1.0001 margin below covers the approximation)
     }
     for (int off = 16; off; off >>= 1) r = fmaxf(r, __shfl_xor_sync(FULL, r, off));
     Capsule c;
     c.r = r * 1.0001f + 1e-6f * (1.f + fabsf(A.x) + fabsf(A.y) + fabsf(A.z));
     float3 Dx = make_float3(B.x - A.x, B.y - A.y, B.z - A.z);
-    c.invD.x = __fdividef(1.f, fabsf(Dx.x) > 1e-30f ? Dx.x : copysignf(1e-30f, Dx.x));
-    c.invD.y = __fdividef(1.f, fabsf(Dx.y) > 1e-30f ? Dx.y : copysignf(1e-30f, Dx.y));
-    c.invD.z = __fdividef(1.f, fabsf(Dx.z) > 1e-30f ? Dx.z : copysignf(1e-30f, Dx.z));
+    c.invD.x = vp_rcp(fabsf(Dx.x) > 1e-30f ? Dx.x : copysignf(1e-30f, Dx.x));
+    c.invD.y = vp_rcp(fabsf(Dx.y) > 1e-30f ? Dx.y : copysignf(1e-30f, Dx.y));
+    c.invD.z = vp_rcp(fabsf(Dx.z) > 1e-30f ? Dx.z : copysignf(1e-30f, Dx.z));
     c.AI = make_float3(A.x * c.invD.x, A.y * c.invD.y, A.z * c.invD.z);
     return c;
 }
@@ -540,7 +541,7 @@ struct TilePrism {
 __device__ __forceinline__ TilePrism tile_prism(bool alive, unsigned am, float3 o0, float3 d, float t0, float t1)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    const float inv_n = __fdividef(1.f, (float)__popc(am));
+    const float inv_n = vp_rcp((float)__popc(am));
     const float3 P0 = make_float3(fmaf(d.x, t0, o0.x), fmaf(d.y, t0, o0.y), fmaf(d.z, t0, o0.z));
     const float3 P1 = make_float3(fmaf(d.x, t1, o0.x), fmaf(d.y, t1, o0.y), fmaf(d.z, t1, o0.z));
     float3 A = alive ? P0 : make_float3(0.f, 0.f, 0.f), B = alive ? P1 : make_float3(0.f, 0.f, 0.f);
@@ -552,7 +553,7 @@ __device__ __forceinline__ TilePrism tile_prism(bool alive, unsigned am, float3 
     TilePrism p;
     p.A = A;
     p.D = make_float3(B.x - A.x, B.y - A.y, B.z - A.z);
-    const float dl = rsqrtf(fmaxf(p.D.x * p.D.x + p.D.y * p.D.y + p.D.z * p.D.z, 1e-30f));
+    const float dl = vp_rsqrt(fmaxf(p.D.x * p.D.x + p.D.y * p.D.y + p.D.z * p.D.z, 1e-30f));
     p.w = make_float3(p.D.x * dl, p.D.y * dl, p.D.z * dl);
     // u: the direction from the tile's first to its last pixel of a row (lanes 0 and 7), made orthogonal to w.  ANY
     // orthonormal frame keeps the bound valid; this one makes it tight for image tiles.
@@ -566,7 +567,7 @@ __device__ __forceinline__ TilePrism tile_prism(bool alive, unsigned am, float3 
         ur = fabsf(p.w.x) < 0.6f ? make_float3(0.f, -p.w.z, p.w.y) : make_float3(-p.w.z, 0.f, p.w.x);
         ul = ur.x * ur.x + ur.y * ur.y + ur.z * ur.z;
     }
-    const float uil = rsqrtf(ul);
+    const float uil = vp_rsqrt(ul);
     p.u = make_float3(ur.x * uil, ur.y * uil, ur.z * uil);
     p.v = make_float3(p.w.y * p.u.z - p.w.z * p.u.y, p.w.z * p.u.x - p.w.x * p.u.z, p.w.x * p.u.y - p.w.y * p.u.x);
     float ra = 0.f, rb = 0.f, rw = 0.f;
@@ -604,7 +605,7 @@ __device__ __forceinline__ bool prism_may_hit(const DevScene &S, int pos, const 
     if (!(dd > 1e-30f)) return true;
 #if VP_APPROX_ORDER
     // approximate reciprocal / root: 2 ulp on k is covered by `err` below, lam only sorts candidates into buckets
-    const float idd = __fdividef(1.f, dd);
+    const float idd = vp_rcp(dd);
     const float k = (Ap.x * Dp.x + Ap.y * Dp.y + Ap.z * Dp.z) * idd;
 #else
     const float k = (Ap.x * Dp.x + Ap.y * Dp.y + Ap.z * Dp.z) / dd;
@@ -615,13 +616,13 @@ __device__ __forceinline__ bool prism_may_hit(const DevScene &S, int pos, const 
     if (!(pl2 > 1.f)) {                     // the mean line itself passes through the bounding ellipsoid
 #if VP_APPROX_ORDER
         const float x = (1.f - pl2) * idd;
-        lam -= x * rsqrtf(fmaxf(x, 1e-37f));
+        lam -= x * vp_rsqrt(fmaxf(x, 1e-37f));
 #else
         lam -= sqrtf((1.f - pl2) / dd);
 #endif
         return true;
     }
-    const float ipl = rsqrtf(pl2), pl = pl2 * ipl;
+    const float ipl = vp_rsqrt(pl2), pl = pl2 * ipl;
     const float3 e = make_float3(P.x * ipl, P.y * ipl, P.z * ipl);
     const float3 g = make_float3(r0.x * e.x + r1.x * e.y + r2.x * e.z, r0.y * e.x + r1.y * e.y + r2.y * e.z,
                                  r0.z * e.x + r1.z * e.y + r2.z * e.z);
@@ -897,10 +898,10 @@ __device__ __forceinline__ void walk_tile(const DevScene &S, int *smem, const fl
         else {
             const float fill_h = (float)found_max * (1.f / (VP_FILL * TILE_HIT_CAP));
             const float fill_c = (float)tcn * (1.f / (float)(VP_CAND_TARGET));
-            const float f_h = (fill_h < 0.15f) ? VP_GROW_MAX : fminf(fmaxf(__fdividef(1.f, fill_h), 0.5f), 2.f);
+            const float f_h = (fill_h < 0.15f) ? VP_GROW_MAX : fminf(fmaxf(vp_rcp(fill_h), 0.5f), 2.f);
             // the candidate count only shrinks the interval while that can help: boxes that contain the whole
             // neighbourhood (nested primitives) stay candidates however short the interval gets
-            const float f_c = fmaxf(__fdividef(1.f, fmaxf(fill_c, 0.25f)), delta > delta0 * (1.f / VP_CSHRINK_FLOOR) ? 0.5f : 1.f);
+            const float f_c = fmaxf(vp_rcp(fmaxf(fill_c, 0.25f)), delta > delta0 * (1.f / VP_CSHRINK_FLOOR) ? 0.5f : 1.f);
             delta = fmaxf(delta * fminf(f_h, f_c), delta_floor);
         }
         t_start = t_done;
@@ -1110,15 +1111,15 @@ __device__ __forceinline__ RfEval rf_eval(float3 o, float3 d, float4 g0, float4 
 template <int KERNEL>
 __device__ __forceinline__ float rf_transmittance(float4 g0, float4 g1, const Isect &is)
 {
-    const float isx = __fdividef(1.f, g1.x), isy = __fdividef(1.f, g1.y), isz = __fdividef(1.f, g1.z);
+    const float isx = vp_rcp(g1.x), isy = vp_rcp(g1.y), isz = vp_rcp(g1.z);
     const float3 oo = make_float3(is.ro.x * isx, is.ro.y * isy, is.ro.z * isz);
     const float3 dd = make_float3(is.rd.x * isx, is.rd.y * isy, is.rd.z * isz);
     const float od = fmaf(oo.x, dd.x, fmaf(oo.y, dd.y, oo.z * dd.z)), dd2 = fmaf(dd.x, dd.x, fmaf(dd.y, dd.y, dd.z * dd.z));
-    const float tp = -__fdividef(od, dd2);
+    const float tp = -od * vp_rcp(dd2);
     const float ux = fmaf(tp, dd.x, oo.x), uy = fmaf(tp, dd.y, oo.y), uz = fmaf(tp, dd.z, oo.z);
     const float q = fmaf(ux, ux, fmaf(uy, uy, uz * uz));
     float G;
-    if (KERNEL == VP_KERNEL_GAUSSIAN) G = __expf(-0.5f * q);
+    if (KERNEL == VP_KERNEL_GAUSSIAN) G = vp_exp(-0.5f * q);
     else G = fmaxf(0.75f * (1.f - q * (1.f / 9.f)), 0.f);
     float a = g0.w * G;
     if (!(a < 0.9999f)) a = 0.9999f;
@@ -1159,10 +1160,10 @@ __device__ __forceinline__ RfEval rf_eval_far(float3 o, float3 d, float4 g0, flo
 {
     RfEval e;
     // approximate reciprocals / ex2 (2 ulp): a value path, nothing here orders hits
-    const float isx = __fdividef(1.f, g1.x), isy = __fdividef(1.f, g1.y), isz = __fdividef(1.f, g1.z);
+    const float isx = vp_rcp(g1.x), isy = vp_rcp(g1.y), isz = vp_rcp(g1.z);
     const float3 rd = rot_t_mul_fast(R, d);
     const float3 dd = make_float3(rd.x * isx, rd.y * isy, rd.z * isz);
-    const float inv_dd2 = __fdividef(1.f, fmaf(dd.x, dd.x, fmaf(dd.y, dd.y, dd.z * dd.z)));
+    const float inv_dd2 = vp_rcp(fmaf(dd.x, dd.x, fmaf(dd.y, dd.y, dd.z * dd.z)));
     float3 ro = rot_t_mul_fast(R, make_float3(o.x - g0.x, o.y - g0.y, o.z - g0.z));
     const float t0 = -fmaf(ro.x * isx, dd.x, fmaf(ro.y * isy, dd.y, ro.z * isz * dd.z)) * inv_dd2;
     const float3 o1 = make_float3(fmaf(d.x, t0, o.x), fmaf(d.y, t0, o.y), fmaf(d.z, t0, o.z));
@@ -1172,7 +1173,7 @@ __device__ __forceinline__ RfEval rf_eval_far(float3 o, float3 d, float4 g0, flo
     const float3 w = rot_t_mul_fast(R, make_float3(e.pp.x - g0.x, e.pp.y - g0.y, e.pp.z - g0.z));
     if (KERNEL == VP_KERNEL_GAUSSIAN) {
         const float ux = w.x * isx, uy = w.y * isy, uz = w.z * isz;
-        e.G = __expf(-0.5f * fmaf(ux, ux, fmaf(uy, uy, uz * uz)));
+        e.G = vp_exp(-0.5f * fmaf(ux, ux, fmaf(uy, uy, uz * uz)));
     } else {
         const float ux = w.x * isx * (1.f / 3.f), uy = w.y * isy * (1.f / 3.f), uz = w.z * isz * (1.f / 3.f);
         e.G = fmaxf(0.75f * (1.f - fmaf(ux, ux, fmaf(uy, uy, uz * uz))), 0.f);
@@ -2141,7 +2142,7 @@ __device__ __forceinline__ void prb_step(float4 st, const float (&g)[3], float (
     const float T = st.w, omt = 1.f - T;
     const float col[3] = { st.x, st.y, st.z };
     // one approximate reciprocal per hit instead of six IEEE divisions (T = 0 -> inf -> NaN below, as the literal form)
-    const float inv_t = __fdividef(1.f, T);
+    const float inv_t = vp_rcp(T);
     dalpha = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
