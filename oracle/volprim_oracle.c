@@ -111,26 +111,30 @@ typedef struct {
 /* dr.quat_to_matrix(q, size=3) with q = (x, y, z, w), NOT normalised (common.py:73,86). */
 static void quat_to_matrix(const REAL q[4], REAL R[3][3])
 {
+    /* Fixed evaluation order with fused multiply-adds (what a GPU backend emits for these expressions): 2 (x y - z w)
+     * = fma(2x, y, -(2z) w) exactly, since scaling by two is exact; 1 - 2 (y y + z z) = fma(-2y, y, fma(-2z, z, 1)). */
     REAL x = q[0], y = q[1], z = q[2], w = q[3];
-    REAL xx = x * x, yy = y * y, zz = z * z;
-    REAL xy = x * y, xz = x * z, yz = y * z;
-    REAL xw = x * w, yw = y * w, zw = z * w;
-    R[0][0] = R_(1) - R_(2) * (yy + zz);
-    R[0][1] = R_(2) * (xy - zw);
-    R[0][2] = R_(2) * (xz + yw);
-    R[1][0] = R_(2) * (xy + zw);
-    R[1][1] = R_(1) - R_(2) * (xx + zz);
-    R[1][2] = R_(2) * (yz - xw);
-    R[2][0] = R_(2) * (xz - yw);
-    R[2][1] = R_(2) * (yz + xw);
-    R[2][2] = R_(1) - R_(2) * (xx + yy);
+    REAL x2 = R_(2) * x, y2 = R_(2) * y, z2 = R_(2) * z;
+    REAL xw = x2 * w, yw = y2 * w, zw = z2 * w;
+    R[0][0] = FMA(-y2, y, FMA(-z2, z, R_(1)));
+    R[0][1] = FMA(x2, y, -zw);
+    R[0][2] = FMA(x2, z, yw);
+    R[1][0] = FMA(x2, y, zw);
+    R[1][1] = FMA(-x2, x, FMA(-z2, z, R_(1)));
+    R[1][2] = FMA(y2, z, -xw);
+    R[2][0] = FMA(x2, z, -yw);
+    R[2][1] = FMA(y2, z, xw);
+    R[2][2] = FMA(-x2, x, FMA(-y2, y, R_(1)));
 }
 
-/* rot.T * v */
+/* a . b in the fixed order fma(a2, b2, fma(a1, b1, a0 b0)) */
+static REAL dot3(const REAL a[3], const REAL b[3]) { return FMA(a[2], b[2], FMA(a[1], b[1], a[0] * b[0])); }
+
+/* rot.T * v, each component a dot3 of a column of R with v */
 static void rot_t_mul(const REAL R[3][3], const REAL v[3], REAL out[3])
 {
     for (int i = 0; i < 3; ++i)
-        out[i] = (R[0][i] * v[0] + R[1][i] * v[1]) + R[2][i] * v[2];
+        out[i] = FMA(R[2][i], v[2], FMA(R[1][i], v[1], R[0][i] * v[0]));
 }
 
 /* mi.math.srgb_to_linear (volprim_rf.py:190) */
@@ -218,12 +222,12 @@ static int ray_ellipsoid(const REAL o[3], const REAL d[3], const ellipsoid *e, R
     rot_t_mul(e->R, d, rd);
     rot_t_mul(e->R, v, ro);
     for (int i = 0; i < 3; ++i) { dd[i] = rd[i] / sc[i]; oo[i] = ro[i] / sc[i]; }
-    REAL a = (dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2];
-    REAL b = -((oo[0] * dd[0] + oo[1] * dd[1]) + oo[2] * dd[2]);
-    REAL c = ((oo[0] * oo[0] + oo[1] * oo[1]) + oo[2] * oo[2]) - R_(1);
+    REAL a = dot3(dd, dd);
+    REAL b = -dot3(oo, dd);
+    REAL c = dot3(oo, oo) - R_(1);
     REAL ba = b / a;
-    REAL l0 = oo[0] + ba * dd[0], l1 = oo[1] + ba * dd[1], l2 = oo[2] + ba * dd[2];
-    REAL discr = R_(1) - ((l0 * l0 + l1 * l1) + l2 * l2);
+    REAL l[3] = { FMA(ba, dd[0], oo[0]), FMA(ba, dd[1], oo[1]), FMA(ba, dd[2], oo[2]) };
+    REAL discr = R_(1) - dot3(l, l);
     if (discr_out) *discr_out = discr;
     return improved_solve_quadratic(a, b, c, discr, tn, tf);
 }
@@ -745,9 +749,29 @@ EXPORT void orc_trace_forward(const orc_scene *sc, const orc_params *pr, int64_t
     }
 }
 
+/* Test aid: with abs mode on, orc_trace_adjoint accumulates the ABSOLUTE value of every per-hit contribution, i.e.
+ * sum_hits |term| per gradient element -- the quantity that bounds the rounding error of an fp32 accumulation of the
+ * same terms (eps * sum |term|), whatever the order.  In the geometry chain the components of R^T (p - c) are
+ * additionally floored at one scale (|u_i| >= 1): the fp32 error of p - c is ABSOLUTE (a few ulp of the world coordinates),
+ * so a term proportional to a small u_i is uncertain by what it would be at |u_i| ~ 1, not by a fraction of itself. */
+static int g_abs_mode = 0;
+EXPORT void orc_set_abs_mode(int on) { g_abs_mode = on; }
+#define ACC(dst, x) do { double x__ = (x); (dst) += g_abs_mode ? fabs(x__) : x__; } while (0)
+
 static void chain_dR_to_quat(const ellipsoid *e, double dR[3][3], double g10[10])
 {
     double x = e->q[0], y = e->q[1], z = e->q[2], w4 = e->q[3];
+    if (g_abs_mode) { /* dR holds magnitudes: every product enters with its absolute value */
+        x = fabs(x); y = fabs(y); z = fabs(z); w4 = fabs(w4);
+        g10[6] += 2 * (y * dR[0][1] + z * dR[0][2] + y * dR[1][0] + 2 * x * dR[1][1] + w4 * dR[1][2] + z * dR[2][0]
+                       + w4 * dR[2][1] + 2 * x * dR[2][2]);
+        g10[7] += 2 * (2 * y * dR[0][0] + x * dR[0][1] + w4 * dR[0][2] + x * dR[1][0] + z * dR[1][2] + w4 * dR[2][0]
+                       + z * dR[2][1] + 2 * y * dR[2][2]);
+        g10[8] += 2 * (2 * z * dR[0][0] + w4 * dR[0][1] + x * dR[0][2] + w4 * dR[1][0] + 2 * z * dR[1][1] + y * dR[1][2]
+                       + x * dR[2][0] + y * dR[2][1]);
+        g10[9] += 2 * (z * dR[0][1] + y * dR[0][2] + z * dR[1][0] + x * dR[1][2] + y * dR[2][0] + x * dR[2][1]);
+        return;
+    }
     g10[6] += 2 * (y * dR[0][1] + z * dR[0][2] + y * dR[1][0] - 2 * x * dR[1][1] - w4 * dR[1][2] + z * dR[2][0]
                    + w4 * dR[2][1] - 2 * x * dR[2][2]);
     g10[7] += 2 * (-2 * y * dR[0][0] + x * dR[0][1] + w4 * dR[0][2] + x * dR[1][0] + z * dR[1][2] - w4 * dR[2][0]
@@ -763,6 +787,21 @@ static void chain_quadratic(const ellipsoid *e, const REAL p[3], REAL k, REAL dq
     REAL v[3] = { p[0] - e->c[0], p[1] - e->c[1], p[2] - e->c[2] }, w[3];
     rot_t_mul(e->R, v, w);
     double dw[3], ds[3];
+    if (g_abs_mode) { /* magnitudes, with |u_i| = |w_i| / (k s_i) floored at 1 and |v_a| at the smallest scale */
+        double smin = fmin(e->s[0], fmin(e->s[1], e->s[2])) * (double)k, dva[3], dRa[3][3];
+        for (int i = 0; i < 3; ++i) {
+            double ks = (double)k * e->s[i], wa = fabs((double)w[i]) + ks;
+            dw[i] = 2.0 * wa / (ks * ks) * fabs((double)dq);
+            ds[i] = 2.0 * wa * wa / (ks * ks * e->s[i]) * fabs((double)dq);
+        }
+        for (int a = 0; a < 3; ++a) {
+            dva[a] = fabs((double)e->R[a][0]) * dw[0] + fabs((double)e->R[a][1]) * dw[1] + fabs((double)e->R[a][2]) * dw[2];
+            for (int b = 0; b < 3; ++b) dRa[a][b] = (fabs((double)v[a]) + smin) * dw[b];
+        }
+        for (int a = 0; a < 3; ++a) { g10[a] += dva[a]; g10[3 + a] += ds[a]; }
+        chain_dR_to_quat(e, dRa, g10);
+        return;
+    }
     for (int i = 0; i < 3; ++i) {
         double ks = (double)k * e->s[i];
         dw[i] = 2.0 * w[i] / (ks * ks) * dq;
@@ -836,12 +875,6 @@ static void chain_density(const ellipsoid *e, int kernel, const REAL o[3], const
  * Gradients are accumulated in double into g_data [n*10], g_attr [n], g_sh [n*C] (caller-zeroed).
  * `state_in` is used as given (the caller decides between reference_exact and corrected, Q3).
  */
-/* Test aid: with abs mode on, orc_trace_adjoint accumulates the ABSOLUTE value of every per-hit contribution, i.e.
- * sum_hits |term| per gradient element -- the quantity that bounds the rounding error of an fp32 accumulation of the
- * same terms (eps * sum |term|), whatever the order. */
-static int g_abs_mode = 0;
-EXPORT void orc_set_abs_mode(int on) { g_abs_mode = on; }
-#define ACC(dst, x) do { double x__ = (x); (dst) += g_abs_mode ? fabs(x__) : x__; } while (0)
 
 EXPORT void orc_trace_adjoint(const orc_scene *sc, const orc_params *pr, int64_t R, const REAL *ray_o,
                               const REAL *ray_d, const REAL *ray_maxt, const REAL *dL, const REAL *state_in,

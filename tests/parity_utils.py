@@ -164,7 +164,10 @@ class GradientReference:
         """(float64 gradients, per-element noise).  noise = |fp32 oracle - float64 oracle| + (SUM_EPS + kappa / 3) *
         sum_hits |term|.  SUM_EPS bounds what an fp32 ACCUMULATION of the per-hit terms loses (the oracles accumulate in
         double; the reference's Dr.Jit scatter-add and the CUDA kernels accumulate in fp32, and with a random delta-L
-        thousands of terms cancel to a small sum); kappa is the primitive's fp32 conditioning (see __init__) -- the
+        thousands of terms cancel to a small sum); kappa is the primitive's fp32 conditioning (see __init__), applied to
+        terms in which the oracle's abs mode floors every |u_i| = |R^T (p - c)|_i / s_i at 1: the error of p - c is a few
+        ulp of the WORLD coordinates, i.e. absolute, so a term that happens to be small because the ray passes the
+        primitive's mid-plane (u_i ~ 0 along a thin axis) is as uncertain as it would be at |u_i| ~ 1 -- the
         observed |fp32 - float64| alone is one realisation of that noise and can be small by luck."""
         g64 = self.o64.adjoint(op, o, d, dL, state, mt)
         g32 = self.o32.adjoint(op, o, d, dL, state, mt)

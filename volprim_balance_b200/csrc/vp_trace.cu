@@ -141,8 +141,7 @@ __device__ __forceinline__ Isect exact_isect(float3 o, float3 d, float4 g0, floa
 #else
     float ba = __fdiv_rn(b, a);
 #endif
-    float3 l = make_float3(__fadd_rn(oo.x, __fmul_rn(ba, dd.x)), __fadd_rn(oo.y, __fmul_rn(ba, dd.y)),
-                           __fadd_rn(oo.z, __fmul_rn(ba, dd.z)));
+    float3 l = make_float3(__fmaf_rn(ba, dd.x, oo.x), __fmaf_rn(ba, dd.y, oo.y), __fmaf_rn(ba, dd.z, oo.z));
     float discr = __fsub_rn(1.f, vp_dot_rn(l, l));
     r.valid = false;
     r.tn = r.tf = 0.f;
