@@ -74,7 +74,18 @@ def _worker(rank, ws, port, q):
         torch.cuda.synchronize()
         g_multi = bucket.flat.clone()
         rms = float(g_single.pow(2).mean().sqrt())
-        err = float(((g_multi - g_single).abs() / (g_single.abs() + rms)).max())
+        rel = (g_multi - g_single).abs() / (g_single.abs() + rms)
+        err = float(rel.max())
+        where = int(rel.argmax())
+        both_s, both_m = [torch.empty_like(g_single) for _ in range(ws)], [torch.empty_like(g_multi) for _ in range(ws)]
+        dist.all_gather(both_s, g_single)
+        dist.all_gather(both_m, g_multi)
+        bad = torch.nonzero(rel > 1e-4).flatten()
+        detail = (f"single-GPU gradients of the ranks differ by {float((both_s[0] - both_s[1]).abs().max()):.3e}, reduced gradients by "
+                  f"{float((both_m[0] - both_m[1]).abs().max()):.3e}; off elements span {int(bad.min()) if len(bad) else -1}.."
+                  f"{int(bad.max()) if len(bad) else -1}; element {where} of {rel.numel()}: sharded {float(g_multi[where]):.6e} single {float(g_single[where]):.6e}, "
+                  f"{int((rel > 1e-4).sum())} elements off, ranges {step.ranges}, record usable {step.record.usable()}, "
+                  f"estimate {step.shape.accel().hits_per_ray_estimate:.1f}")
         # (3) full steps: replicas must stay BIT-identical (same reduced gradient, same Adam, deterministic rebuild)
         losses = []
         for _ in range(3):
@@ -88,7 +99,7 @@ def _worker(rank, ws, port, q):
         full = vp.render(scene, sensor=sensors[1], spp=1, jitter=False)
         tiled = parallel.render_tiles(scene, sensors[1], vp.render, spp=1, jitter=False)
         tiles_ok = True if rank != 0 else bool(torch.equal(tiled, full))
-        q.put((rank, err, identical, losses, tiles_ok, step.timing))
+        q.put((rank, err, identical, losses, tiles_ok, dict(step.timing, detail=detail)))
         dist.destroy_process_group()
     except Exception as e:  # noqa: BLE001
         import traceback
@@ -113,7 +124,7 @@ def test_sharded_training_step_equals_single_gpu_and_replicas_stay_identical():
     for r in res:
         assert r[1] != "error", r[2]
     for rank, err, identical, losses, tiles_ok, timing in res:
-        assert err < 1e-4, f"rank {rank}: reduced gradient differs from the single-GPU gradient ({err:.2e})"
+        assert err < 1e-4, f"rank {rank}: reduced gradient differs from the single-GPU gradient ({err:.2e}; {timing.get('detail')})"
         assert identical, "replicas diverged after optimiser step + rebuild"
         assert tiles_ok
         assert losses[-1] < losses[0]

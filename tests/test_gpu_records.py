@@ -50,6 +50,25 @@ def test_fused_raygen_equals_explicit_rays(spp, jitter):
     assert torch.equal(c.rgb, b.rgb[16 * 64 * spp:40 * 64 * spp])
 
 
+def test_repeated_builds_are_bit_reproducible():
+    """Replicas of a multi-GPU job build their own LBVH; everything the walk derives from the build (initial interval
+    width, tile-vs-per-ray heuristic) must come out bit-identical however the build's warps were scheduled -- otherwise
+    fragile rays order their hits differently from replica to replica.  Eight independent builds of one cloud render
+    one view to the same bits (the sums the build takes over all leaves are integer accumulations)."""
+    cloud = synthetic.make_cloud(60_000, synthetic.sigma0_for_hits(60_000, 30.0), seed=11)
+    cam = synthetic.ring_camera(3, 8, 128, 96)
+    p, _ = make_params(0, 0, 64)
+    ref = None
+    for _ in range(8):
+        acc = gpu_scene(cloud)
+        r = acc.render_forward(p, RaySource(camera=_sensor(cam).vp_camera()))
+        got = (r.rgb.clone(), r.beta.clone(), r.nhits.clone())
+        if ref is None:
+            ref = got
+        assert all(torch.equal(a, b) for a, b in zip(ref, got))
+        del acc
+
+
 @pytest.mark.parametrize("scratch", [None, 1 << 20])
 def test_compressed_hit_records_equal_the_dense_lists(scratch):
     """vp_render_forward(record): ray_offsets = exclusive scan of the hit counts, ids = the dense lists without padding,

@@ -261,10 +261,15 @@ __global__ void k_gather_soa(const float *__restrict__ data10, const float *__re
         half = (ex + ey + ez) * (1.f / 6.f);
     }
     }
+    // The two sums are accumulated as 64-bit fixed-point integers (2^-32 units): integer addition is associative, so the
+    // build is bit-reproducible whatever order the warps arrive in.  (A float atomicAdd here made delta0 differ in its
+    // last bits from run to run, and with it the interval partition -- and the hit order of fragile rays -- between the
+    // replicas of a multi-GPU job.)
     for (int off = 16; off; off >>= 1) area += __shfl_xor_sync(0xffffffffu, area, off);
-    if ((threadIdx.x & 31) == 0 && area > 0.f) atomicAdd(info + 7, area);
     for (int off = 16; off; off >>= 1) half += __shfl_xor_sync(0xffffffffu, half, off);
-    if ((threadIdx.x & 31) == 0 && half > 0.f) atomicAdd(info + 8, half);
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(info + 12);
+    if ((threadIdx.x & 31) == 0 && area > 0.f) atomicAdd(acc, (unsigned long long)fmin((double)area * 4294967296.0, 1.8e19));
+    if ((threadIdx.x & 31) == 0 && half > 0.f) atomicAdd(acc + 1, (unsigned long long)fmin((double)half * 4294967296.0, 1.8e19));
 }
 
 // scene box (union of the root's child boxes, or the single leaf) and the initial interval width
@@ -286,7 +291,10 @@ __global__ void k_scene_info(int n, const float *__restrict__ nodes, const float
     float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
     float diag = sqrtf(ex * ex + ey * ey + ez * ez);
     float vol = ex * ey * ez;
-    float area = info[7];
+    const unsigned long long *acc = reinterpret_cast<const unsigned long long *>(info + 12);
+    float area = (float)((double)acc[0] * (1.0 / 4294967296.0));
+    info[7] = area;
+    info[8] = (float)((double)acc[1] * (1.0 / 4294967296.0));
     float delta0 = diag * (1.f / 64.f);
     if (vol > 0.f && area > 0.f && isfinite(vol) && isfinite(area)) delta0 = 2.f * 12.f * vol / area;
     if (!(delta0 > 0.f) || !isfinite(delta0)) delta0 = 1.f;
@@ -407,7 +415,7 @@ int vp_build_impl(vp_ctx *ctx, bool refit_only, cudaStream_t st)
     if ((rc = vp_ensure(ctx, ctx->geo2, sizeof(float4) * n))) return rc;
     if ((rc = vp_ensure(ctx, ctx->sh4, sizeof(float4) * (size_t)n * (sh_stride4 > 0 ? sh_stride4 : 1)))) return rc;
     if ((rc = vp_ensure(ctx, ctx->xf, sizeof(float4) * 3 * (size_t)n))) return rc;
-    if ((rc = vp_ensure(ctx, ctx->info, sizeof(float) * 12))) return rc;
+    if ((rc = vp_ensure(ctx, ctx->info, sizeof(float) * 16))) return rc;
     if ((rc = vp_ensure(ctx, ctx->nodes, sizeof(float) * 16 * (size_t)(n > 1 ? n - 1 : 1)))) return rc;
     if ((rc = vp_ensure(ctx, ctx->perm, sizeof(int32_t) * n))) return rc;
     if ((rc = vp_ensure(ctx, ctx->inv_perm, sizeof(int32_t) * n))) return rc;
@@ -452,7 +460,7 @@ int vp_build_impl(vp_ctx *ctx, bool refit_only, cudaStream_t st)
         order = (const uint32_t *)ctx->perm.ptr;  // perm holds the same values (int32 >= 0)
     }
 
-    VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->info.ptr, 0, sizeof(float) * 12, st));
+    VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->info.ptr, 0, sizeof(float) * 16, st));
     k_gather_soa<<<cdiv(n, B), B, 0, st>>>(data10, attr, sh, n, ctx->sh_floats, sh_stride4, ctx->extent, order,
                                            (float4 *)ctx->geo0.ptr, (float4 *)ctx->geo1.ptr, (float4 *)ctx->geo2.ptr,
                                            (float4 *)ctx->sh4.ptr, (float4 *)ctx->xf.ptr, (float *)ctx->info.ptr,

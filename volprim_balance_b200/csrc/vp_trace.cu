@@ -26,6 +26,7 @@
 //   retry with a shorter interval; below a minimum width the per-ray walker runs a plain closest-hit search per step.
 // The adjoint either replays recorded hit lists (no BVH access) or re-traces like the primal.
 #include "vp_internal.cuh"
+#include <cstdlib>
 #include "vp_scan.cuh"
 
 #include <cfloat>
@@ -2775,6 +2776,10 @@ int vp_adjoint_begin_impl(vp_ctx *ctx, const vp_params *p_in, const vp_ray_sourc
         if ((rc = vp_ensure(ctx, ctx->scan_tmp, sizeof(uint64_t) * (size_t)(vpscan::n_tiles(n) + 1)))) return rc;
         uint32_t *offsets = (uint32_t *)ctx->adj_offsets.ptr, *extra = (uint32_t *)ctx->adj_extra.ptr;
         VP_CUDA_CHECK(ctx, cudaMemsetAsync(offsets, 0, sizeof(uint32_t) * (size_t)(n + 1), st));
+        // debugging aid (VOLPRIM_POISON=1): every bucket slot starts as NaN, so a slot the ray pass failed to write shows
+        // up as a NaN gradient instead of silently reusing what an earlier pass left there
+        static const bool poison = std::getenv("VOLPRIM_POISON") != nullptr;
+        if (poison) VP_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->adj_state.ptr, 0xff, 2 * sizeof(float4) * (size_t)rec->capacity, st));
         if (n > 0) {
             int64_t blocks = (rec->capacity + 255) / 256;
             if (blocks > 148 * 32) blocks = 148 * 32;
