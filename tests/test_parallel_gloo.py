@@ -29,6 +29,24 @@ def test_shards_partition_views_and_rows():
         assert max(rows) - min(rows) <= 4 * k + 4
 
 
+def test_tapered_ranges_tile_the_primitives_and_shrink():
+    """RefineStep's all-reduce ranges: contiguous, 4-aligned boundaries, sizes falling towards the end (the last range's
+    all-reduce is the exposed one), degenerate counts handled."""
+    for n, k in ((1_000_000, 4), (30_000, 3), (1001, 6), (7, 4), (4, 1), (0, 3)):
+        r = parallel.chunk_ranges(n, k, taper=True)
+        if n == 0:
+            assert r == []
+            continue
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(p0 % 4 == 0 for p0, _ in r) and all(p1 > p0 for p0, p1 in r) and len(r) <= k
+        sizes = [p1 - p0 for p0, p1 in r]
+        assert all(a >= b - 4 for a, b in zip(sizes, sizes[1:]))
+        if n >= 1000 and len(r) == k and k > 1:
+            assert sizes[-1] < n / k          # smaller than an even split
+        b = parallel.GradientBucket(n, 12, "cpu", ranges=r)
+        assert b.flat.numel() >= n * (10 + 1 + 12)
+
+
 def test_packed_gradient_segments_are_aligned_and_ranges_tile():
     for n in (11, 12, 1001):
         g = {"data": torch.arange(n * 10.0), "opacities": torch.arange(n * 1.0), "sh_coeffs": torch.arange(n * 27.0)}
